@@ -1,0 +1,226 @@
+/*
+ * b200nav.h -- C ABI of the B200-native HIMM mapping + VFH+ steering path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point names
+ * the reference interface it replaces (paths relative to the reference root jmloveyj/ros_navigation).
+ * The host side of the reference (ROS nodes, MapProvider, Steerer) keeps calling its own classes; thin
+ * C++ shims with the reference's class interfaces (include/b200nav_shim.hpp) forward to these functions.
+ *
+ * Conventions
+ *  - Every function returns B200NAV_OK (0) or a negative B200NAV_E* code; b200nav_last_error() gives text.
+ *    No exceptions, no callbacks cross the boundary.  CUDA errors never abort the process.
+ *  - The caller owns every buffer it passes.  "host" pointers are ordinary (ideally pinned) host memory,
+ *    "dev" pointers are device memory on the context's device.
+ *  - Calls on one context are NOT internally locked: serialise them externally, exactly as the reference
+ *    serialises map access with MapProvider::mapMutex_ (move_control/src/map_provider.cpp:197).
+ *  - All work is enqueued on the context's CUDA stream; entry points that return results to host memory
+ *    synchronise that stream before returning, the *_dev variants do not.
+ *  - Layers are grid_map::Matrix-compatible: column-major float, rows x cols, NaN = unknown
+ *    (grid_map_core/include/grid_map_core/TypeDefs.hpp:16).  With n_robots > 1 a layer is one allocation
+ *    [robot][col][row].
+ *  - There is no CPU fallback: without a CUDA device b200nav_ctx_create fails with B200NAV_ENODEVICE.
+ */
+#ifndef B200NAV_H
+#define B200NAV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NAV_VERSION 100
+
+enum {
+  B200NAV_OK = 0,
+  B200NAV_EINVAL = -1,    /* bad argument                                  */
+  B200NAV_ECUDA = -2,     /* CUDA runtime error (see b200nav_last_error)   */
+  B200NAV_ENOMEM = -3,    /* host or device allocation failed              */
+  B200NAV_ENOLAYER = -4,  /* unknown layer name                            */
+  B200NAV_ERANGE = -5,    /* size outside supported limits                 */
+  B200NAV_ENODEVICE = -6  /* no usable CUDA device                         */
+};
+
+typedef struct b200nav_ctx b200nav_ctx;
+typedef struct b200nav_grid b200nav_grid;
+typedef struct b200nav_vfh b200nav_vfh;
+
+/* ------------------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL
+ * to let the context create its own non-blocking stream. */
+int b200nav_ctx_create(int device, void* cuda_stream, b200nav_ctx** out);
+int b200nav_ctx_destroy(b200nav_ctx* ctx);
+int b200nav_ctx_synchronize(b200nav_ctx* ctx);
+void* b200nav_ctx_stream(b200nav_ctx* ctx);
+/* Last error text of this context (ctx == NULL: of the calling thread's last failed create call). */
+const char* b200nav_last_error(b200nav_ctx* ctx);
+/* Number of kernels this context launched since creation (bench.py's gpu_launches). */
+int64_t b200nav_ctx_launch_count(b200nav_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Grid: device-resident grid_map::GridMap layers for n_robots independent maps of identical size.
+ * Replaces the data side of grid_map::GridMap as used by MapProvider (map_provider.cpp:17-41,145-149).
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* GridMap::setGeometry (grid_map_core/src/GridMap.cpp:51-70): rows = round(len_x/res), cols = round(len_y/res),
+ * length = size*res, startIndex = 0; same position for every robot (change with b200nav_grid_set_geometry). */
+int b200nav_grid_create(b200nav_ctx* ctx, double len_x, double len_y, double res, double pos_x, double pos_y,
+                        int n_robots, b200nav_grid** out);
+int b200nav_grid_destroy(b200nav_grid* grid);
+int b200nav_grid_size(const b200nav_grid* grid, int* rows, int* cols, int* n_robots);
+/* GridMap::add(layer) with NaN fill (MapUpdater ctor, move_control/include/move_control/map_updater.h:10-14). */
+int b200nav_grid_add_layer(b200nav_grid* grid, const char* name);
+/* Make `alias` name the same device memory as `target` (zero-copy form of map_["master"] = map_["laser"],
+ * map_provider.cpp:221).  */
+int b200nav_grid_alias_layer(b200nav_grid* grid, const char* alias, const char* target);
+/* map_[dst] = map_[src] for all robots (map_provider.cpp:221, the copying form). */
+int b200nav_grid_copy_layer(b200nav_grid* grid, const char* dst, const char* src);
+/* GridMap::clear(layer) / clearAll (GridMap.cpp:605-629): NaN fill.  layer == NULL clears every layer. */
+int b200nav_grid_clear(b200nav_grid* grid, const char* layer);
+/* Whole-layer transfer for one robot; `colmajor` is rows*cols floats laid out like Eigen::MatrixXf::data(). */
+int b200nav_grid_upload(b200nav_grid* grid, int robot, const char* layer, const float* colmajor);
+int b200nav_grid_download(b200nav_grid* grid, int robot, const char* layer, float* colmajor);
+/* position_ / startIndex_ of one robot's map (GridMap::setPosition, GridMap.hpp:499-516). */
+int b200nav_grid_set_geometry(b200nav_grid* grid, int robot, double pos_x, double pos_y, int start0, int start1);
+int b200nav_grid_get_geometry(const b200nav_grid* grid, int robot, double* pos_x, double* pos_y, int* start0,
+                              int* start1);
+/* GridMap::move(position) (GridMap.cpp:346-412): circular-buffer shift + NaN-fill of the dropped strips in
+ * every layer.  *moved = 1 if the start index changed. */
+int b200nav_grid_move(b200nav_grid* grid, int robot, double x, double y, int* moved);
+/* GridMapRosConverter::toOccupancyGrid (grid_map_ros/src/GridMapRosConverter.cpp:251-287): int8 [-1,0..100],
+ * reversed cell order, unwrapped index.  out_host = rows*cols bytes. */
+int b200nav_grid_to_occupancy(b200nav_grid* grid, int robot, const char* layer, float data_min, float data_max,
+                              int8_t* out_host);
+/* Device pointer of a layer ([robot][col][row] floats) for zero-copy consumers. */
+void* b200nav_grid_layer_devptr(b200nav_grid* grid, const char* layer);
+
+/* ------------------------------------------------------------------------------------------------------
+ * HIMM update.  Replaces LaserMapUpdater::updateMap / RangeMapUpdater::updateMap
+ * (move_control/src/laser_map_updater.cpp:7-21, range_map_updater.cpp:7-21) and MapUpdater::lineOnMap /
+ * clearCell / markCell (map_updater.h:38-71) including grid_map::LineIterator
+ * (grid_map_core/src/iterators/LineIterator.cpp:16-150).
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* MapUpdater::RangeSample (map_updater.h:28-32): map-frame metres. */
+typedef struct {
+  double sx, sy;      /* start  */
+  double ex, ey;      /* end    */
+  int32_t clear_end;  /* ifClearEnd: non-zero = do not mark the end cell */
+  int32_t reserved;
+} b200nav_sample;
+
+/* Apply n samples IN ORDER to layer `layer` of robot `robot`.  bbox = {minX,minY,maxX,maxY}, in/out, updated
+ * like MapUpdater::touch (map_updater.h:73-78); may be NULL.  Result is bit-identical to the reference. */
+int b200nav_himm_update(b200nav_grid* grid, int robot, const char* layer, const b200nav_sample* host_samples, int n,
+                        double* bbox);
+/* Batched: samples of robot r are host_samples[offsets[r] .. offsets[r+1]) (offsets has n_robots+1 entries),
+ * each robot's samples applied in order to its own map.  bbox: n_robots*4 doubles in/out, or NULL. */
+int b200nav_himm_update_batched(b200nav_grid* grid, const char* layer, const b200nav_sample* host_samples,
+                                const int32_t* host_offsets, double* bbox);
+/* Same with samples/offsets already in device memory; asynchronous (no stream sync).  total = offsets[n_robots]. */
+int b200nav_himm_update_batched_dev(b200nav_grid* grid, const char* layer, const b200nav_sample* dev_samples,
+                                    const int32_t* dev_offsets, int total);
+
+/* ------------------------------------------------------------------------------------------------------
+ * VFH+.  Replaces move_control::VFH (move_control/include/move_control/vfh.h:182-361,
+ * move_control/src/vfh.cpp) and Steerer::getRangesFromSubmap (move_control/src/steerer.cpp:147-191).
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* The 19 VFH constructor arguments (vfh.h:185-203) + SetRobotRadius + the Steerer constants. */
+typedef struct {
+  double cell_size;                     /* mm                                   */
+  int32_t window_diameter;              /* cells                                */
+  int32_t sector_angle;                 /* deg                                  */
+  double safety_dist_0ms;               /* mm                                   */
+  double safety_dist_1ms;
+  int32_t max_speed;                    /* mm/s                                 */
+  int32_t max_speed_narrow_opening;
+  int32_t max_speed_wide_opening;
+  int32_t max_acceleration;             /* mm/s^2                               */
+  int32_t min_turnrate;                 /* deg/s (unused by the algorithm)      */
+  int32_t max_turnrate_0ms;
+  int32_t max_turnrate_1ms;
+  int32_t reserved0;
+  double min_turn_radius_safety_factor;
+  double free_space_cutoff_0ms;
+  double obs_cutoff_0ms;
+  double free_space_cutoff_1ms;
+  double obs_cutoff_1ms;
+  double weight_desired_dir;
+  double weight_current_dir;
+  double robot_radius;                  /* mm, VFH::SetRobotRadius              */
+  double submap_length;                 /* m, Steerer: Length(1.5,1.5) (steerer.cpp:158) */
+  double occupied_threshold;            /* cells with value <= this are free (steerer.cpp:167: 3) */
+} b200nav_vfh_params;
+
+/* Steerer::initVfh defaults (steerer.cpp:69-121). */
+void b200nav_vfh_default_params(b200nav_vfh_params* p);
+
+/* Per-robot inputs of one decision (Steerer::update, steerer.cpp:221-263). */
+typedef struct {
+  double x, y, yaw;         /* robot pose in the map frame (MapProvider::getRobotPos)        */
+  double dt;                /* seconds since the previous update (reference: gettimeofday)   */
+  int32_t current_speed;    /* mm/s                                                          */
+  float goal_direction;     /* deg, 0 = robot's right, 90 = ahead                            */
+  float goal_distance;      /* mm                                                            */
+  float goal_tolerance;     /* mm                                                            */
+} b200nav_vfh_input;
+
+/* Per-robot result; the 16-byte record that batched mode all-gathers. */
+typedef struct {
+  int32_t speed;            /* chosen_speed, mm/s     */
+  int32_t turnrate;         /* chosen_turnrate, deg/s */
+  float picked_angle;       /* VFH::GetPickedAngle    */
+  uint32_t flags;           /* B200NAV_CMD_* bits     */
+} b200nav_command;
+
+#define B200NAV_CMD_EMERGENCY 1u   /* obstacle inside the safety distance (vfh.cpp:1020-1034) */
+#define B200NAV_CMD_HEMMED_IN 2u   /* no candidate direction (vfh.cpp:720-728)                */
+#define B200NAV_CMD_CANT_TURN 4u   /* Cant_Turn_To_Goal (vfh.cpp:612-654)                     */
+#define B200NAV_CMD_NO_SUBMAP 8u   /* window could not be formed; treated as no obstacles     */
+
+/* VFH::VFH + SetRobotRadius + Init for n_robots independent controllers sharing one parameter set
+ * (vfh.cpp:53-110,237-416). */
+int b200nav_vfh_create(b200nav_ctx* ctx, const b200nav_vfh_params* p, int n_robots, b200nav_vfh** out);
+int b200nav_vfh_destroy(b200nav_vfh* vfh);
+/* VFH::SetCurrentMaxSpeed (vfh.cpp:144-166). */
+int b200nav_vfh_set_current_max_speed(b200nav_vfh* vfh, int max_speed);
+int b200nav_vfh_hist_size(const b200nav_vfh* vfh);       /* VFH::getHistSize        */
+int b200nav_vfh_num_tables(const b200nav_vfh* vfh);      /* NUM_CELL_SECTOR_TABLES  */
+int b200nav_vfh_get_max_turnrate(const b200nav_vfh* vfh, int speed); /* VFH::GetMaxTurnrate (vfh.cpp:130-138) */
+
+/* VFH::Update_VFH (vfh.cpp:480-605) for one robot with a host pseudo-scan double[361][2].
+ * `in->x,y,yaw` are ignored. */
+int b200nav_vfh_update_ranges(b200nav_vfh* vfh, int robot, const double* ranges361x2, const b200nav_vfh_input* in,
+                              b200nav_command* out);
+/* Steerer::getRangesFromSubmap + VFH::Update_VFH fused, reading layer `layer` of the device grid. */
+int b200nav_vfh_update_grid(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer, int robot,
+                            const b200nav_vfh_input* in, b200nav_command* out);
+/* All robots; host arrays of n_robots entries. */
+int b200nav_vfh_update_batched(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
+                               const b200nav_vfh_input* host_in, b200nav_command* host_out);
+/* Same with device arrays; asynchronous. */
+int b200nav_vfh_update_batched_dev(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
+                                   const b200nav_vfh_input* dev_in, b200nav_command* dev_out);
+
+/* Read back per-robot state after an update (any pointer may be NULL):
+ *  origin_hist / hist / last_binary: hist_size floats (VFH::OriginHist, VFH::Hist, Last_Binary_Hist);
+ *  scalars[4] = {Picked_Angle, Last_Picked_Angle, Desired_Angle, Blocked_Circle_Radius};
+ *  ints[2]    = {last_chosen_speed, Max_Speed_For_Picked_Angle}. */
+int b200nav_vfh_read_state(b200nav_vfh* vfh, int robot, float* origin_hist, float* hist, float* last_binary,
+                           float* scalars, int32_t* ints);
+/* The pseudo-scan (double[361][2], column 1 = 0) the last *_grid update of this robot built. */
+int b200nav_vfh_read_ranges(b200nav_vfh* vfh, int robot, double* ranges361x2);
+/* Tables built by Init, for parity checks: per cell [x][y] (W*W): direction, distance, base magnitude;
+ * sector masks of table `table`: W*W*nwords uint32 (nwords = (hist_size+31)/32); min_turning_radius:
+ * current_max_speed+1 ints.  Any pointer may be NULL. */
+int b200nav_vfh_get_tables(const b200nav_vfh* vfh, int table, float* dir, float* dist, float* base_mag,
+                           uint32_t* sector_masks, int32_t* min_turning_radius);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NAV_H */

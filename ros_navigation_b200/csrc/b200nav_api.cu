@@ -1,0 +1,939 @@
+/*
+ * b200nav_api.cu -- implementation of the C ABI declared in include/b200nav.h.
+ *
+ * Host logic only: contexts, device buffers, launch configuration, error plumbing.  All compute runs in the
+ * sm_100a kernels of himm_kernels.cuh / vfh_kernels.cuh / grid_kernels.cuh; there is no CPU fallback.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nav.h"
+#include "geometry.h"
+#include "grid_kernels.cuh"
+#include "himm_kernels.cuh"
+#include "vfh_kernels.cuh"
+#include "vfh_tables.h"
+
+using namespace b200nav;
+
+/* ================================================================================================================
+ * Objects
+ * ============================================================================================================== */
+
+struct b200nav_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  int64_t launches = 0;
+  int sm_count = 0;
+  char err[512] = {0};
+};
+
+namespace {
+
+thread_local char g_err[512] = {0};
+
+int set_err(b200nav_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return set_err(ctx, e__ == cudaErrorMemoryAllocation ? B200NAV_ENOMEM : B200NAV_ECUDA, "%s: %s", #expr, \
+                     cudaGetErrorString(e__));                                                           \
+  } while (0)
+
+/* Grow-only device buffer. */
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    want = (want * 5) / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Layer {
+  float* dev = nullptr;
+  bool owned = true;
+};
+
+}  // namespace
+
+struct b200nav_grid {
+  b200nav_ctx* ctx = nullptr;
+  GridDims dims;
+  int n_robots = 1;
+  std::vector<RobotGeom> geom_host;
+  RobotGeom* geom_dev = nullptr;
+  std::map<std::string, Layer> layers;
+  DevBuf samples, segs, offsets, occ;
+  size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
+};
+
+struct b200nav_vfh {
+  b200nav_ctx* ctx = nullptr;
+  b200nav_vfh_params params;
+  VfhTables tab;
+  int n_robots = 1;
+  VfhDev dev;
+  /* device tables */
+  float *d_dir = nullptr, *d_dist = nullptr, *d_base = nullptr;
+  double* d_thr = nullptr;
+  int16_t* d_kidx = nullptr;
+  uint32_t* d_masks = nullptr;
+  int32_t* d_mtr = nullptr;
+  DevBuf in_buf, out_buf, ranges_buf;
+  /* TMA descriptor cache: one per (layer pointer, geometry) */
+  const float* tmap_layer = nullptr;
+  int tmap_rows = 0, tmap_cols = 0, tmap_robots = 0, tmap_box_r = 0, tmap_box_c = 0;
+  CUtensorMap tmap;
+  bool tmap_valid = false;
+  bool tma_disabled = false;
+};
+
+namespace {
+
+int sync_stream(b200nav_ctx* ctx) {
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200NAV_OK;
+}
+
+int check_launch(b200nav_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(ctx, B200NAV_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  ctx->launches++;
+  return B200NAV_OK;
+}
+
+Layer* find_layer(b200nav_grid* g, const char* name) {
+  if (!name) return nullptr;
+  auto it = g->layers.find(name);
+  return it == g->layers.end() ? nullptr : &it->second;
+}
+
+int fill_nan(b200nav_grid* g, float* p, size_t n) {
+  const int threads = 256;
+  const size_t blocks = std::min<size_t>((n + threads - 1) / threads, (size_t)g->ctx->sm_count * 16);
+  grid_fill_kernel<<<(unsigned)std::max<size_t>(blocks, 1), threads, 0, g->ctx->stream>>>(p, n, nanf(""));
+  return check_launch(g->ctx, "grid_fill_kernel");
+}
+
+int upload_geom(b200nav_grid* g) {
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(g->geom_dev, g->geom_host.data(), sizeof(RobotGeom) * g->n_robots,
+                                   cudaMemcpyHostToDevice, g->ctx->stream));
+  /* geom_host may be modified right after return: make the copy complete first (tiny, rare). */
+  return sync_stream(g->ctx);
+}
+
+constexpr int kVfhMaxSmem = 200 * 1024;
+
+/* ---- HIMM launch ------------------------------------------------------------------------------------------- */
+constexpr int kSub = 64, kWR = 2, kWC = 2, kListCap = 2048;
+using TileCfg = HimmTileCfg<kSub, kWR, kWC, kListCap>;
+
+int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
+                int robot0, int n_active, int single_n, int total) {
+  b200nav_ctx* ctx = g->ctx;
+  if (total <= 0) return B200NAV_OK;
+  CUDA_TRY(ctx, g->segs.reserve(sizeof(BeamSeg) * (size_t)total));
+  HimmArgs a;
+  a.dims = g->dims;
+  a.geom = g->geom_dev;
+  a.layer = layer;
+  a.samples = dev_samples;
+  a.offsets = dev_offsets;
+  a.segs = static_cast<BeamSeg*>(g->segs.p);
+  a.robot0 = robot0;
+  a.n_active = n_active;
+  a.single_n = single_n;
+  a.total = total;
+  a.tiles_r = (g->dims.rows + TileCfg::kTileR - 1) / TileCfg::kTileR;
+  a.tiles_c = (g->dims.cols + TileCfg::kTileC - 1) / TileCfg::kTileC;
+  himm_prep_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(a);
+  int rc = check_launch(ctx, "himm_prep_kernel");
+  if (rc) return rc;
+  auto kern = himm_tile_kernel<kSub, kWR, kWC, kListCap>;
+  dim3 grid((unsigned)(a.tiles_r * a.tiles_c), (unsigned)n_active);
+  kern<<<grid, TileCfg::kThreads, TileCfg::kSmemBytes, ctx->stream>>>(a);
+  return check_launch(ctx, "himm_tile_kernel");
+}
+
+void host_touch(const b200nav_sample* s, int n, double* bbox) {
+  /* MapUpdater::touch (map_updater.h:73-78) over start and end of every sample */
+  for (int i = 0; i < n; i++) {
+    bbox[0] = std::min(bbox[0], s[i].sx);
+    bbox[1] = std::min(bbox[1], s[i].sy);
+    bbox[2] = std::max(bbox[2], s[i].sx);
+    bbox[3] = std::max(bbox[3], s[i].sy);
+    bbox[0] = std::min(bbox[0], s[i].ex);
+    bbox[1] = std::min(bbox[1], s[i].ey);
+    bbox[2] = std::max(bbox[2], s[i].ex);
+    bbox[3] = std::max(bbox[3], s[i].ey);
+  }
+}
+
+/* ---- VFH helpers -------------------------------------------------------------------------------------------- */
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+/* Window box for the VFH stage-R TMA load: (box_r x box_c) floats starting at the window's top-left cell. */
+void vfh_window_box(const b200nav_vfh* v, const b200nav_grid* g, int& box_r, int& box_c) {
+  const int n = (int)ceil(v->tab.c.submap_length / g->dims.res) + 2;
+  box_c = std::min(n, g->dims.cols);
+  box_r = std::min((n + 3) & ~3, (g->dims.rows + 3) & ~3);
+}
+
+bool vfh_prepare_tmap(b200nav_vfh* v, b200nav_grid* g, const float* layer, int box_r, int box_c) {
+  if (v->tma_disabled) return false;
+  if (g->dims.rows % 4 != 0 || box_r > 256 || box_c > 256) return false;
+  if (v->tmap_valid && v->tmap_layer == layer && v->tmap_rows == g->dims.rows && v->tmap_cols == g->dims.cols &&
+      v->tmap_robots == g->n_robots && v->tmap_box_r == box_r && v->tmap_box_c == box_c)
+    return true;
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)g->dims.rows, (cuuint64_t)g->dims.cols, (cuuint64_t)g->n_robots};
+  const cuuint64_t gstride[2] = {(cuuint64_t)g->dims.rows * sizeof(float),
+                                 (cuuint64_t)g->dims.rows * g->dims.cols * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)box_r, (cuuint32_t)box_c, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(&v->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(layer), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+  if (r != CUDA_SUCCESS) return false;
+  v->tmap_valid = true;
+  v->tmap_layer = layer;
+  v->tmap_rows = g->dims.rows;
+  v->tmap_cols = g->dims.cols;
+  v->tmap_robots = g->n_robots;
+  v->tmap_box_r = box_r;
+  v->tmap_box_c = box_c;
+  return true;
+}
+
+size_t vfh_smem_bytes(const b200nav_vfh* v, bool from_grid, int box_r, int box_c) {
+  size_t b = from_grid ? (((size_t)box_r * box_c * sizeof(float) + 127) & ~(size_t)127) : 0;
+  b += sizeof(double) * (B200NAV_NRANGES + 1);
+  b += sizeof(float) * ((v->tab.c.hist_size + 1) & ~1);
+  b += sizeof(uint16_t) * (size_t)v->dev.nf + 16;
+  return b;
+}
+
+int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const float* layer, const b200nav_vfh_input* dev_in,
+               const double* dev_ranges, b200nav_command* dev_out, int robot0, int n) {
+  b200nav_ctx* ctx = v->ctx;
+  VfhGridArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  size_t smem;
+  if (g) {
+    int box_r, box_c;
+    vfh_window_box(v, g, box_r, box_c);
+    ga.dims = g->dims;
+    ga.geom = g->geom_dev;
+    ga.layer = layer;
+    ga.box_r = box_r;
+    ga.box_c = box_c;
+    ga.use_tma = vfh_prepare_tmap(v, g, layer, box_r, box_c) ? 1 : 0;
+    if (ga.use_tma) tm = v->tmap;
+    smem = vfh_smem_bytes(v, true, box_r, box_c);
+    if (smem > (size_t)kVfhMaxSmem) return set_err(ctx, B200NAV_ERANGE, "VFH window too large for shared memory (%zu B)", smem);
+    auto kern = vfh_update_kernel<true>;
+    kern<<<n, B200NAV_VFH_THREADS, smem, ctx->stream>>>(v->dev, ga, tm, dev_in, nullptr, dev_out, robot0);
+  } else {
+    smem = vfh_smem_bytes(v, false, 0, 0);
+    auto kern = vfh_update_kernel<false>;
+    kern<<<n, B200NAV_VFH_THREADS, smem, ctx->stream>>>(v->dev, ga, tm, dev_in, dev_ranges, dev_out, robot0);
+  }
+  return check_launch(ctx, "vfh_update_kernel");
+}
+
+/* Opt in to > 48 KB dynamic shared memory once per device (attributes are per device). */
+int configure_kernels(b200nav_ctx* ctx) {
+  CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_kernel<kSub, kWR, kWC, kListCap>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
+  return B200NAV_OK;
+}
+
+template <class T>
+int upload_vec(b200nav_ctx* ctx, T** dst, const std::vector<T>& src) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+  if (!src.empty()) CUDA_TRY(ctx, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return B200NAV_OK;
+}
+
+}  // namespace
+
+/* ================================================================================================================
+ * Context
+ * ============================================================================================================== */
+extern "C" {
+
+int b200nav_ctx_create(int device, void* cuda_stream, b200nav_ctx** out) {
+  if (!out) return set_err(nullptr, B200NAV_EINVAL, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return set_err(nullptr, B200NAV_ENODEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "count == 0");
+  if (device < 0 || device >= count) return set_err(nullptr, B200NAV_EINVAL, "device %d out of range [0,%d)", device, count);
+  std::unique_ptr<b200nav_ctx> ctx(new b200nav_ctx());
+  ctx->device = device;
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_err(nullptr, B200NAV_ENODEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device,
+                   prop.major, prop.minor);
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cuda_stream) {
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  } else {
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->owns_stream = true;
+  }
+  int rc = configure_kernels(ctx.get());
+  if (rc) {
+    snprintf(g_err, sizeof(g_err), "%s", ctx->err);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    return rc;
+  }
+  *out = ctx.release();
+  return B200NAV_OK;
+}
+
+int b200nav_ctx_destroy(b200nav_ctx* ctx) {
+  if (!ctx) return B200NAV_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return B200NAV_OK;
+}
+
+int b200nav_ctx_synchronize(b200nav_ctx* ctx) {
+  if (!ctx) return B200NAV_EINVAL;
+  return sync_stream(ctx);
+}
+
+void* b200nav_ctx_stream(b200nav_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+const char* b200nav_last_error(b200nav_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int64_t b200nav_ctx_launch_count(b200nav_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ================================================================================================================
+ * Grid
+ * ============================================================================================================== */
+
+int b200nav_grid_create(b200nav_ctx* ctx, double len_x, double len_y, double res, double pos_x, double pos_y,
+                        int n_robots, b200nav_grid** out) {
+  if (!ctx || !out) return B200NAV_EINVAL;
+  *out = nullptr;
+  if (!(len_x > 0) || !(len_y > 0) || !(res > 0) || n_robots < 1)
+    return set_err(ctx, B200NAV_EINVAL, "grid_create: length/resolution must be > 0 and n_robots >= 1");
+  const double fr = round(len_x / res), fc = round(len_y / res);
+  if (fr < 1 || fc < 1 || fr > 32767 || fc > 32767)
+    return set_err(ctx, B200NAV_ERANGE, "grid_create: %g x %g cells outside [1, 32767]", fr, fc);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<b200nav_grid> g(new b200nav_grid());
+  g->ctx = ctx;
+  g->dims.rows = (int)fr;
+  g->dims.cols = (int)fc;
+  g->dims.res = res;
+  g->dims.len_x = (double)g->dims.rows * res;
+  g->dims.len_y = (double)g->dims.cols * res;
+  g->n_robots = n_robots;
+  RobotGeom rg;
+  rg.pos_x = pos_x;
+  rg.pos_y = pos_y;
+  rg.start0 = rg.start1 = 0;
+  g->geom_host.assign(n_robots, rg);
+  CUDA_TRY(ctx, cudaMalloc((void**)&g->geom_dev, sizeof(RobotGeom) * n_robots));
+  int rc = upload_geom(g.get());
+  if (rc) {
+    cudaFree(g->geom_dev);
+    return rc;
+  }
+  *out = g.release();
+  return B200NAV_OK;
+}
+
+int b200nav_grid_destroy(b200nav_grid* g) {
+  if (!g) return B200NAV_OK;
+  cudaSetDevice(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  for (auto& kv : g->layers)
+    if (kv.second.owned && kv.second.dev) cudaFree(kv.second.dev);
+  if (g->geom_dev) cudaFree(g->geom_dev);
+  g->samples.release();
+  g->segs.release();
+  g->offsets.release();
+  g->occ.release();
+  delete g;
+  return B200NAV_OK;
+}
+
+int b200nav_grid_size(const b200nav_grid* g, int* rows, int* cols, int* n_robots) {
+  if (!g) return B200NAV_EINVAL;
+  if (rows) *rows = g->dims.rows;
+  if (cols) *cols = g->dims.cols;
+  if (n_robots) *n_robots = g->n_robots;
+  return B200NAV_OK;
+}
+
+int b200nav_grid_add_layer(b200nav_grid* g, const char* name) {
+  if (!g || !name || !*name) return B200NAV_EINVAL;
+  if (find_layer(g, name)) return B200NAV_OK; /* map_.exists(typeName) (map_updater.h:12) */
+  CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
+  Layer l;
+  CUDA_TRY(g->ctx, cudaMalloc((void**)&l.dev, g->layer_elems() * sizeof(float)));
+  int rc = fill_nan(g, l.dev, g->layer_elems());
+  if (rc) {
+    cudaFree(l.dev);
+    return rc;
+  }
+  g->layers[name] = l;
+  return B200NAV_OK;
+}
+
+int b200nav_grid_alias_layer(b200nav_grid* g, const char* alias, const char* target) {
+  if (!g || !alias || !target) return B200NAV_EINVAL;
+  Layer* t = find_layer(g, target);
+  if (!t) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", target);
+  Layer* a = find_layer(g, alias);
+  if (a && a->owned && a->dev && a->dev != t->dev) {
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(a->dev);
+  }
+  Layer l;
+  l.dev = t->dev;
+  l.owned = false;
+  g->layers[alias] = l;
+  return B200NAV_OK;
+}
+
+int b200nav_grid_copy_layer(b200nav_grid* g, const char* dst, const char* src) {
+  if (!g) return B200NAV_EINVAL;
+  Layer *d = find_layer(g, dst), *s = find_layer(g, src);
+  if (!d || !s) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", !d ? dst : src);
+  if (d->dev == s->dev) return B200NAV_OK;
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(d->dev, s->dev, g->layer_elems() * sizeof(float), cudaMemcpyDeviceToDevice,
+                                   g->ctx->stream));
+  return B200NAV_OK;
+}
+
+int b200nav_grid_clear(b200nav_grid* g, const char* layer) {
+  if (!g) return B200NAV_EINVAL;
+  if (layer) {
+    Layer* l = find_layer(g, layer);
+    if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer);
+    return fill_nan(g, l->dev, g->layer_elems());
+  }
+  for (auto& kv : g->layers)
+    if (kv.second.owned) {
+      int rc = fill_nan(g, kv.second.dev, g->layer_elems());
+      if (rc) return rc;
+    }
+  return B200NAV_OK;
+}
+
+int b200nav_grid_upload(b200nav_grid* g, int robot, const char* layer, const float* colmajor) {
+  if (!g || !colmajor || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  const size_t n = (size_t)g->dims.rows * g->dims.cols;
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(l->dev + n * robot, colmajor, n * sizeof(float), cudaMemcpyHostToDevice,
+                                   g->ctx->stream));
+  return sync_stream(g->ctx);
+}
+
+int b200nav_grid_download(b200nav_grid* g, int robot, const char* layer, float* colmajor) {
+  if (!g || !colmajor || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  const size_t n = (size_t)g->dims.rows * g->dims.cols;
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(colmajor, l->dev + n * robot, n * sizeof(float), cudaMemcpyDeviceToHost,
+                                   g->ctx->stream));
+  return sync_stream(g->ctx);
+}
+
+int b200nav_grid_set_geometry(b200nav_grid* g, int robot, double pos_x, double pos_y, int start0, int start1) {
+  if (!g || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  if (start0 < 0 || start0 >= g->dims.rows || start1 < 0 || start1 >= g->dims.cols)
+    return set_err(g->ctx, B200NAV_EINVAL, "start index (%d,%d) outside the buffer", start0, start1);
+  RobotGeom& rg = g->geom_host[robot];
+  rg.pos_x = pos_x;
+  rg.pos_y = pos_y;
+  rg.start0 = start0;
+  rg.start1 = start1;
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(g->geom_dev + robot, &rg, sizeof(RobotGeom), cudaMemcpyHostToDevice,
+                                   g->ctx->stream));
+  return sync_stream(g->ctx);
+}
+
+int b200nav_grid_get_geometry(const b200nav_grid* g, int robot, double* pos_x, double* pos_y, int* start0,
+                              int* start1) {
+  if (!g || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  const RobotGeom& rg = g->geom_host[robot];
+  if (pos_x) *pos_x = rg.pos_x;
+  if (pos_y) *pos_y = rg.pos_y;
+  if (start0) *start0 = rg.start0;
+  if (start1) *start1 = rg.start1;
+  return B200NAV_OK;
+}
+
+int b200nav_grid_move(b200nav_grid* g, int robot, double x, double y, int* moved) {
+  if (!g || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  /* GridMap::move (GridMap.cpp:346-412).  The index/position bookkeeping is a handful of scalar operations and
+   * stays on the host (the GridMap object owns its geometry); the strips that fall out of the map are NaN-filled
+   * on the device in every layer. */
+  RobotGeom& rg = g->geom_host[robot];
+  const double res = g->dims.res;
+  const double t[2] = {(x - rg.pos_x) / res, (y - rg.pos_y) / res};
+  int shift[2];
+  for (int i = 0; i < 2; i++) shift[i] = -(int)(t[i] + 0.5 * (t[i] > 0 ? 1 : -1));
+  const int size[2] = {g->dims.rows, g->dims.cols};
+  int start[2] = {rg.start0, rg.start1};
+  const size_t per_robot = (size_t)g->dims.rows * g->dims.cols;
+  auto clear_strip = [&](int axis, int index, int n) -> int {
+    if (n <= 0) return B200NAV_OK;
+    for (auto& kv : g->layers) {
+      if (!kv.second.owned) continue;
+      float* base = kv.second.dev + per_robot * robot;
+      const int r0 = axis == 0 ? index : 0, nr = axis == 0 ? n : g->dims.rows;
+      const int c0 = axis == 1 ? index : 0, nc = axis == 1 ? n : g->dims.cols;
+      dim3 grid((unsigned)((nr + 127) / 128), (unsigned)std::min(nc, 65535));
+      grid_fill_rect_kernel<<<grid, 128, 0, g->ctx->stream>>>(base, g->dims.rows, r0, nr, c0, nc, nanf(""));
+      int rc = check_launch(g->ctx, "grid_fill_rect_kernel");
+      if (rc) return rc;
+    }
+    return B200NAV_OK;
+  };
+  for (int i = 0; i < 2; i++) {
+    if (shift[i] == 0) continue;
+    if (abs(shift[i]) >= size[i]) {
+      int rc = clear_strip(0, 0, g->dims.rows);
+      if (rc) return rc;
+    } else {
+      const int sign = (shift[i] > 0 ? 1 : -1);
+      const int start_index = start[i] - (sign < 0 ? 1 : 0);
+      const int end_index = start_index - sign + shift[i];
+      const int n_cells = abs(shift[i]);
+      int index = (sign > 0 ? start_index : end_index);
+      wrap_index(index, size[i]);
+      if (index + n_cells <= size[i]) {
+        int rc = clear_strip(i, index, n_cells);
+        if (rc) return rc;
+      } else {
+        const int first_n = size[i] - index;
+        int rc = clear_strip(i, index, first_n);
+        if (rc) return rc;
+        rc = clear_strip(i, 0, n_cells - first_n);
+        if (rc) return rc;
+      }
+    }
+  }
+  rg.start0 += shift[0];
+  rg.start1 += shift[1];
+  wrap_index(rg.start0, g->dims.rows);
+  wrap_index(rg.start1, g->dims.cols);
+  rg.pos_x += (double)(-shift[0]) * res;
+  rg.pos_y += (double)(-shift[1]) * res;
+  if (moved) *moved = (shift[0] != 0 || shift[1] != 0) ? 1 : 0;
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(g->geom_dev + robot, &rg, sizeof(RobotGeom), cudaMemcpyHostToDevice,
+                                   g->ctx->stream));
+  return sync_stream(g->ctx);
+}
+
+int b200nav_grid_to_occupancy(b200nav_grid* g, int robot, const char* layer, float data_min, float data_max,
+                              int8_t* out_host) {
+  if (!g || !out_host || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  const size_t n = (size_t)g->dims.rows * g->dims.cols;
+  CUDA_TRY(g->ctx, g->occ.reserve(n));
+  const RobotGeom& rg = g->geom_host[robot];
+  const int threads = 256;
+  grid_to_occupancy_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, g->ctx->stream>>>(
+      l->dev + n * robot, g->dims.rows, g->dims.cols, rg.start0, rg.start1, data_min, data_max,
+      static_cast<int8_t*>(g->occ.p));
+  int rc = check_launch(g->ctx, "grid_to_occupancy_kernel");
+  if (rc) return rc;
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(out_host, g->occ.p, n, cudaMemcpyDeviceToHost, g->ctx->stream));
+  return sync_stream(g->ctx);
+}
+
+void* b200nav_grid_layer_devptr(b200nav_grid* g, const char* layer) {
+  if (!g) return nullptr;
+  Layer* l = find_layer(g, layer);
+  return l ? l->dev : nullptr;
+}
+
+/* ================================================================================================================
+ * HIMM
+ * ============================================================================================================== */
+
+int b200nav_himm_update(b200nav_grid* g, int robot, const char* layer, const b200nav_sample* host_samples, int n,
+                        double* bbox) {
+  if (!g || robot < 0 || robot >= g->n_robots || n < 0 || (n > 0 && !host_samples)) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  if (n == 0) return B200NAV_OK;
+  b200nav_ctx* ctx = g->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, g->samples.reserve(sizeof(b200nav_sample) * (size_t)n));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_samples, sizeof(b200nav_sample) * (size_t)n,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  int rc = himm_launch(g, l->dev, static_cast<const b200nav_sample*>(g->samples.p), nullptr, robot, 1, n, n);
+  if (rc) return rc;
+  if (bbox) host_touch(host_samples, n, bbox); /* overlaps the kernels */
+  return sync_stream(ctx);
+}
+
+int b200nav_himm_update_batched(b200nav_grid* g, const char* layer, const b200nav_sample* host_samples,
+                                const int32_t* host_offsets, double* bbox) {
+  if (!g || !host_offsets) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  b200nav_ctx* ctx = g->ctx;
+  const int nr = g->n_robots;
+  if (host_offsets[0] != 0) return set_err(ctx, B200NAV_EINVAL, "offsets[0] must be 0");
+  for (int r = 0; r < nr; r++)
+    if (host_offsets[r + 1] < host_offsets[r]) return set_err(ctx, B200NAV_EINVAL, "offsets must be non-decreasing");
+  const int total = host_offsets[nr];
+  if (total == 0) return B200NAV_OK;
+  if (!host_samples) return B200NAV_EINVAL;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, g->samples.reserve(sizeof(b200nav_sample) * (size_t)total));
+  CUDA_TRY(ctx, g->offsets.reserve(sizeof(int32_t) * (size_t)(nr + 1)));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_samples, sizeof(b200nav_sample) * (size_t)total,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->offsets.p, host_offsets, sizeof(int32_t) * (size_t)(nr + 1),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  int rc = himm_launch(g, l->dev, static_cast<const b200nav_sample*>(g->samples.p),
+                       static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total);
+  if (rc) return rc;
+  if (bbox)
+    for (int r = 0; r < nr; r++)
+      host_touch(host_samples + host_offsets[r], host_offsets[r + 1] - host_offsets[r], bbox + 4 * r);
+  return sync_stream(ctx);
+}
+
+int b200nav_himm_update_batched_dev(b200nav_grid* g, const char* layer, const b200nav_sample* dev_samples,
+                                    const int32_t* dev_offsets, int total) {
+  if (!g || !dev_offsets || total < 0 || (total > 0 && !dev_samples)) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
+  return himm_launch(g, l->dev, dev_samples, dev_offsets, 0, g->n_robots, -1, total);
+}
+
+/* ================================================================================================================
+ * VFH+
+ * ============================================================================================================== */
+
+void b200nav_vfh_default_params(b200nav_vfh_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  /* Steerer::initVfh (steerer.cpp:69-121) */
+  p->cell_size = 100;
+  p->window_diameter = 30;
+  p->sector_angle = 5;
+  p->safety_dist_0ms = 10;
+  p->safety_dist_1ms = 50;
+  p->max_speed = 200;
+  p->max_speed_narrow_opening = 200;
+  p->max_speed_wide_opening = 300;
+  p->max_acceleration = 200;
+  p->min_turnrate = 40;
+  p->max_turnrate_0ms = 40;
+  p->max_turnrate_1ms = 40;
+  p->min_turn_radius_safety_factor = 1.0;
+  p->free_space_cutoff_0ms = 2000000.0;
+  p->obs_cutoff_0ms = 4000000.0;
+  p->free_space_cutoff_1ms = 2000000.0;
+  p->obs_cutoff_1ms = 4000000.0;
+  p->weight_desired_dir = 10.0;
+  p->weight_current_dir = 1.0;
+  p->robot_radius = 178.0;
+  p->submap_length = 1.5;
+  p->occupied_threshold = 3.0;
+}
+
+static int vfh_reset_state(b200nav_vfh* v) {
+  /* VFH ctor + Init (vfh.cpp:90-95, 258-262): Hist = OriginHist = 0, Last_Binary_Hist = 1, angles 90, speed 0 */
+  b200nav_ctx* ctx = v->ctx;
+  const size_t H = v->tab.c.hist_size, n = v->n_robots;
+  std::vector<float> ones(H * n, 1.0f);
+  CUDA_TRY(ctx, cudaMemset(v->dev.origin_hist, 0, sizeof(float) * H * n));
+  CUDA_TRY(ctx, cudaMemset(v->dev.hist, 0, sizeof(float) * H * n));
+  CUDA_TRY(ctx, cudaMemcpy(v->dev.last_binary, ones.data(), sizeof(float) * H * n, cudaMemcpyHostToDevice));
+  VfhRobotState s0;
+  s0.picked = s0.last_picked = s0.desired = 90.f;
+  s0.blocked_radius = 0.f; /* uninitialised in the reference; defined as 0 */
+  s0.last_chosen_speed = 0;
+  s0.max_speed_for_picked = 0;
+  std::vector<VfhRobotState> st(n, s0);
+  CUDA_TRY(ctx, cudaMemcpy(v->dev.st, st.data(), sizeof(VfhRobotState) * n, cudaMemcpyHostToDevice));
+  std::vector<double> r(n * B200NAV_NRANGES, 5000.0);
+  CUDA_TRY(ctx, cudaMemcpy(v->dev.ranges, r.data(), sizeof(double) * r.size(), cudaMemcpyHostToDevice));
+  return B200NAV_OK;
+}
+
+int b200nav_vfh_create(b200nav_ctx* ctx, const b200nav_vfh_params* p, int n_robots, b200nav_vfh** out) {
+  if (!ctx || !p || !out || n_robots < 1) return B200NAV_EINVAL;
+  *out = nullptr;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<b200nav_vfh> v(new b200nav_vfh());
+  v->ctx = ctx;
+  v->params = *p;
+  v->n_robots = n_robots;
+  int rc = vfh_build_tables(*p, v->tab, ctx->err, sizeof(ctx->err));
+  if (rc) return rc;
+  const VfhTables& t = v->tab;
+  if ((size_t)t.c.front_rows * t.c.window > 65535)
+    return set_err(ctx, B200NAV_ERANGE, "VFH window too large (%d front cells > 65535)", t.c.front_rows * t.c.window);
+  if ((rc = upload_vec(ctx, &v->d_dir, t.dir))) return rc;
+  if ((rc = upload_vec(ctx, &v->d_dist, t.dist))) return rc;
+  if ((rc = upload_vec(ctx, &v->d_base, t.base))) return rc;
+  if ((rc = upload_vec(ctx, &v->d_thr, t.thr))) return rc;
+  if ((rc = upload_vec(ctx, &v->d_kidx, t.kidx))) return rc;
+  if ((rc = upload_vec(ctx, &v->d_masks, t.masks))) return rc;
+  if ((rc = upload_vec(ctx, &v->d_mtr, t.min_turning_radius))) return rc;
+  VfhDev& d = v->dev;
+  memset(&d, 0, sizeof(d));
+  d.c = t.c;
+  d.nf = t.c.front_rows * t.c.window;
+  d.dir = v->d_dir;
+  d.dist = v->d_dist;
+  d.base = v->d_base;
+  d.thr = v->d_thr;
+  d.kidx = v->d_kidx;
+  d.masks = v->d_masks;
+  d.mtr = v->d_mtr;
+  const size_t H = t.c.hist_size;
+  CUDA_TRY(ctx, cudaMalloc((void**)&d.origin_hist, sizeof(float) * H * n_robots));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d.hist, sizeof(float) * H * n_robots));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d.last_binary, sizeof(float) * H * n_robots));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d.st, sizeof(VfhRobotState) * n_robots));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d.ranges, sizeof(double) * B200NAV_NRANGES * n_robots));
+  if ((rc = vfh_reset_state(v.get()))) return rc;
+  *out = v.release();
+  return B200NAV_OK;
+}
+
+int b200nav_vfh_destroy(b200nav_vfh* v) {
+  if (!v) return B200NAV_OK;
+  cudaSetDevice(v->ctx->device);
+  cudaStreamSynchronize(v->ctx->stream);
+  cudaFree(v->d_dir);
+  cudaFree(v->d_dist);
+  cudaFree(v->d_base);
+  cudaFree(v->d_thr);
+  cudaFree(v->d_kidx);
+  cudaFree(v->d_masks);
+  cudaFree(v->d_mtr);
+  cudaFree(v->dev.origin_hist);
+  cudaFree(v->dev.hist);
+  cudaFree(v->dev.last_binary);
+  cudaFree(v->dev.st);
+  cudaFree(v->dev.ranges);
+  v->in_buf.release();
+  v->out_buf.release();
+  v->ranges_buf.release();
+  delete v;
+  return B200NAV_OK;
+}
+
+int b200nav_vfh_set_current_max_speed(b200nav_vfh* v, int max_speed) {
+  if (!v || max_speed < 1) return B200NAV_EINVAL;
+  CUDA_TRY(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+  vfh_build_min_turning_radius(v->tab, v->params, max_speed);
+  int rc = upload_vec(v->ctx, &v->d_mtr, v->tab.min_turning_radius);
+  if (rc) return rc;
+  v->dev.mtr = v->d_mtr;
+  v->dev.c = v->tab.c;
+  return B200NAV_OK;
+}
+
+int b200nav_vfh_hist_size(const b200nav_vfh* v) { return v ? v->tab.c.hist_size : B200NAV_EINVAL; }
+int b200nav_vfh_num_tables(const b200nav_vfh* v) { return v ? v->tab.c.num_tables : B200NAV_EINVAL; }
+int b200nav_vfh_get_max_turnrate(const b200nav_vfh* v, int speed) {
+  return v ? vfh_get_max_turnrate(v->tab.c.max_turnrate_0ms, v->tab.c.max_turnrate_1ms, speed) : B200NAV_EINVAL;
+}
+
+static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int robot0, int n,
+                        const b200nav_vfh_input* host_in, const double* host_ranges, b200nav_command* host_out) {
+  b200nav_ctx* ctx = v->ctx;
+  const float* lay = nullptr;
+  if (g) {
+    if (g->ctx != ctx) return set_err(ctx, B200NAV_EINVAL, "grid and vfh belong to different contexts");
+    if (robot0 + n > g->n_robots) return set_err(ctx, B200NAV_EINVAL, "robot index beyond the grid's robots");
+    Layer* l = find_layer(g, layer);
+    if (!l) return set_err(ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+    lay = l->dev;
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, v->in_buf.reserve(sizeof(b200nav_vfh_input) * (size_t)n));
+  CUDA_TRY(ctx, v->out_buf.reserve(sizeof(b200nav_command) * (size_t)n));
+  CUDA_TRY(ctx, cudaMemcpyAsync(v->in_buf.p, host_in, sizeof(b200nav_vfh_input) * (size_t)n, cudaMemcpyHostToDevice,
+                                ctx->stream));
+  const double* dr = nullptr;
+  if (host_ranges) {
+    CUDA_TRY(ctx, v->ranges_buf.reserve(sizeof(double) * 2 * B200NAV_NRANGES * (size_t)n));
+    CUDA_TRY(ctx, cudaMemcpyAsync(v->ranges_buf.p, host_ranges, sizeof(double) * 2 * B200NAV_NRANGES * (size_t)n,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    dr = static_cast<const double*>(v->ranges_buf.p);
+  }
+  int rc = vfh_launch(v, g, lay, static_cast<const b200nav_vfh_input*>(v->in_buf.p), dr,
+                      static_cast<b200nav_command*>(v->out_buf.p), robot0, n);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(host_out, v->out_buf.p, sizeof(b200nav_command) * (size_t)n, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  return sync_stream(ctx);
+}
+
+int b200nav_vfh_update_ranges(b200nav_vfh* v, int robot, const double* ranges361x2, const b200nav_vfh_input* in,
+                              b200nav_command* out) {
+  if (!v || !ranges361x2 || !in || !out || robot < 0 || robot >= v->n_robots) return B200NAV_EINVAL;
+  return vfh_run_host(v, nullptr, nullptr, robot, 1, in, ranges361x2, out);
+}
+
+int b200nav_vfh_update_grid(b200nav_vfh* v, b200nav_grid* g, const char* layer, int robot,
+                            const b200nav_vfh_input* in, b200nav_command* out) {
+  if (!v || !g || !in || !out || robot < 0 || robot >= v->n_robots) return B200NAV_EINVAL;
+  return vfh_run_host(v, g, layer, robot, 1, in, nullptr, out);
+}
+
+int b200nav_vfh_update_batched(b200nav_vfh* v, b200nav_grid* g, const char* layer, const b200nav_vfh_input* host_in,
+                               b200nav_command* host_out) {
+  if (!v || !g || !host_in || !host_out) return B200NAV_EINVAL;
+  if (g->n_robots != v->n_robots) return set_err(v->ctx, B200NAV_EINVAL, "grid and vfh robot counts differ");
+  return vfh_run_host(v, g, layer, 0, v->n_robots, host_in, nullptr, host_out);
+}
+
+int b200nav_vfh_update_batched_dev(b200nav_vfh* v, b200nav_grid* g, const char* layer,
+                                   const b200nav_vfh_input* dev_in, b200nav_command* dev_out) {
+  if (!v || !g || !dev_in || !dev_out) return B200NAV_EINVAL;
+  if (g->n_robots != v->n_robots) return set_err(v->ctx, B200NAV_EINVAL, "grid and vfh robot counts differ");
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(v->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  CUDA_TRY(v->ctx, cudaSetDevice(v->ctx->device));
+  return vfh_launch(v, g, l->dev, dev_in, nullptr, dev_out, 0, v->n_robots);
+}
+
+int b200nav_vfh_read_state(b200nav_vfh* v, int robot, float* origin_hist, float* hist, float* last_binary,
+                           float* scalars, int32_t* ints) {
+  if (!v || robot < 0 || robot >= v->n_robots) return B200NAV_EINVAL;
+  b200nav_ctx* ctx = v->ctx;
+  const size_t H = v->tab.c.hist_size;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (origin_hist)
+    CUDA_TRY(ctx, cudaMemcpy(origin_hist, v->dev.origin_hist + H * robot, sizeof(float) * H, cudaMemcpyDeviceToHost));
+  if (hist) CUDA_TRY(ctx, cudaMemcpy(hist, v->dev.hist + H * robot, sizeof(float) * H, cudaMemcpyDeviceToHost));
+  if (last_binary)
+    CUDA_TRY(ctx, cudaMemcpy(last_binary, v->dev.last_binary + H * robot, sizeof(float) * H, cudaMemcpyDeviceToHost));
+  if (scalars || ints) {
+    VfhRobotState s;
+    CUDA_TRY(ctx, cudaMemcpy(&s, v->dev.st + robot, sizeof(s), cudaMemcpyDeviceToHost));
+    if (scalars) {
+      scalars[0] = s.picked;
+      scalars[1] = s.last_picked;
+      scalars[2] = s.desired;
+      scalars[3] = s.blocked_radius;
+    }
+    if (ints) {
+      ints[0] = s.last_chosen_speed;
+      ints[1] = s.max_speed_for_picked;
+    }
+  }
+  return B200NAV_OK;
+}
+
+int b200nav_vfh_read_ranges(b200nav_vfh* v, int robot, double* ranges361x2) {
+  if (!v || !ranges361x2 || robot < 0 || robot >= v->n_robots) return B200NAV_EINVAL;
+  double tmp[B200NAV_NRANGES];
+  CUDA_TRY(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+  CUDA_TRY(v->ctx, cudaMemcpy(tmp, v->dev.ranges + (size_t)B200NAV_NRANGES * robot, sizeof(tmp), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < B200NAV_NRANGES; i++) {
+    ranges361x2[2 * i] = tmp[i];
+    ranges361x2[2 * i + 1] = 0.0;
+  }
+  return B200NAV_OK;
+}
+
+int b200nav_vfh_get_tables(const b200nav_vfh* v, int table, float* dir, float* dist, float* base_mag,
+                           uint32_t* sector_masks, int32_t* min_turning_radius) {
+  if (!v || table < 0 || table >= v->tab.c.num_tables) return B200NAV_EINVAL;
+  const VfhTables& t = v->tab;
+  const size_t ww = (size_t)t.c.window * t.c.window;
+  if (dir) memcpy(dir, t.dir_xy.data(), ww * sizeof(float));
+  if (dist) memcpy(dist, t.dist_xy.data(), ww * sizeof(float));
+  if (base_mag) memcpy(base_mag, t.base_xy.data(), ww * sizeof(float));
+  if (sector_masks)
+    memcpy(sector_masks, t.masks_xy.data() + (size_t)table * ww * t.c.nwords, ww * t.c.nwords * sizeof(uint32_t));
+  if (min_turning_radius)
+    memcpy(min_turning_radius, t.min_turning_radius.data(), t.min_turning_radius.size() * sizeof(int32_t));
+  return B200NAV_OK;
+}
+
+/* Test hook (not part of the drop-in surface): force the coalesced-load window path instead of TMA. */
+int b200nav_vfh_debug_disable_tma(b200nav_vfh* v, int disable) {
+  if (!v) return B200NAV_EINVAL;
+  v->tma_disabled = disable != 0;
+  return B200NAV_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,472 @@
+/*
+ * vfh_kernels.cuh -- VFH+ steering decision on sm_100a, one CTA per robot, all stages fused.
+ *
+ * Replaces (behaviour, not code):
+ *   Steerer::getRangesFromSubmap            move_control/src/steerer.cpp:147-191   (stage R)
+ *   VFH::Update_VFH and its callees         move_control/src/vfh.cpp:480-605
+ *     Calculate_Cells_Mag                   :986-1049   (stage M)
+ *     Build_Primary_Polar_Histogram         :1057-1095  (stage H)
+ *     Build_Binary_Polar_Histogram          :1102-1121  (stage B)
+ *     Build_Masked_Polar_Histogram          :1131-1213  (stage K)
+ *     Select_Direction / Select_Candidate_Angle / Cant_Turn_To_Goal / Set_Motion
+ *                                           :755-870, :715-749, :612-654, :1222-1261 (stage S)
+ *
+ * Numerics: all float/double expressions keep the reference's C++ promotions and evaluation order and the file is
+ * compiled with --fmad=false.  The primary histogram is summed by one thread per sector over the occupied cells in
+ * the reference's (y outer, x inner) order, so it is bit-identical, not just within tolerance.  phi_left/phi_right
+ * are order-free max/min and use a warp-shuffle + shared-memory reduction.
+ * The active window is staged into shared memory by TMA (cp.async.bulk.tensor) when the layer pitch allows it
+ * (rows % 4 == 0 and the window does not wrap the circular buffer), otherwise by coalesced loads.
+ */
+#ifndef B200NAV_VFH_KERNELS_CUH
+#define B200NAV_VFH_KERNELS_CUH
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/b200nav.h"
+#include "geometry.h"
+#include "vfh_tables.h"
+
+namespace b200nav {
+
+struct VfhRobotState {
+  float picked, last_picked, desired, blocked_radius;
+  int last_chosen_speed, max_speed_for_picked;
+};
+
+struct VfhDev {
+  VfhConst c;
+  int nf; /* front cells = front_rows * window */
+  const float* dir;
+  const float* dist;
+  const float* base;
+  const double* thr;
+  const int16_t* kidx;
+  const uint32_t* masks; /* [table][f][nwords] */
+  const int32_t* mtr;    /* Min_Turning_Radius[0..current_max_speed] */
+  /* per-robot state */
+  float* origin_hist;    /* [n][H] */
+  float* hist;           /* [n][H] */
+  float* last_binary;    /* [n][H] */
+  VfhRobotState* st;     /* [n]    */
+  double* ranges;        /* [n][361] pseudo-scan of the last update */
+};
+
+struct VfhGridArgs {
+  GridDims dims;
+  const RobotGeom* geom;
+  const float* layer;
+  int box_r, box_c; /* TMA box (floats) = smem window pitch / columns */
+  int use_tma;
+};
+
+#define B200NAV_VFH_THREADS 128
+#define B200NAV_NRANGES 361
+
+/* ---- reference helper expressions (same promotions as vfh.cpp) ------------------------------------------------ */
+__device__ __forceinline__ int vfh_max_turnrate(const VfhConst& c, int speed) {
+  int val = (c.max_turnrate_0ms - (int)(speed * (c.max_turnrate_0ms - c.max_turnrate_1ms) / 1000.0));
+  return val < 0 ? 0 : val;
+}
+__device__ __forceinline__ int vfh_safety_dist(const VfhConst& c, int speed) {
+  int val = (int)(c.safety_dist_0ms + (int)(speed * (c.safety_dist_1ms - c.safety_dist_0ms) / 1000.0));
+  return val < 0 ? 0 : val;
+}
+__device__ __forceinline__ float vfh_bin_low(const VfhConst& c, int speed) {
+  return (float)(c.bin_low_0ms - (speed * (c.bin_low_0ms - c.bin_low_1ms) / 1000.0));
+}
+__device__ __forceinline__ float vfh_bin_high(const VfhConst& c, int speed) {
+  return (float)(c.bin_high_0ms - (speed * (c.bin_high_0ms - c.bin_high_1ms) / 1000.0));
+}
+__device__ __forceinline__ int vfh_speed_index(const VfhConst& c, int speed) {
+  int val = (int)floorf(((float)speed / (float)c.current_max_speed) * c.num_tables);
+  return val >= c.num_tables ? c.num_tables - 1 : val;
+}
+__device__ __forceinline__ float vfh_delta_angle(float a1, float a2) {
+  float diff = a2 - a1;
+  if (diff > 180) diff -= 360;
+  else if (diff < -180) diff += 360;
+  return diff;
+}
+/* glibc hypotf: (float)sqrt((double)x*x + (double)y*y) - products exact, one rounding in the sum, IEEE sqrt. */
+__device__ __forceinline__ float vfh_hypotf(float x, float y) {
+  return (float)sqrt((double)x * (double)x + (double)y * (double)y);
+}
+
+/* Positive doubles order like their bit patterns: shared-memory atomicMin on the pattern is an exact min. */
+__device__ __forceinline__ void atomic_min_pos_double(double* addr, double v) {
+  atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+/* ----------------------------------------------------------------------------------------------------------------
+ * Fused kernel.  FROM_GRID: build the pseudo-scan from the grid window (stage R), else take dev_ranges.
+ * Dynamic shared memory layout (bytes): ranges[361] double | nz[nf] u16 | hist[H] float | window floats (TMA).
+ * -------------------------------------------------------------------------------------------------------------- */
+template <bool FROM_GRID>
+__global__ void __launch_bounds__(B200NAV_VFH_THREADS)
+vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ CUtensorMap tmap,
+                  const b200nav_vfh_input* __restrict__ in, const double* __restrict__ dev_ranges,
+                  b200nav_command* __restrict__ out, int robot0) {
+  extern __shared__ __align__(128) unsigned char vfh_smem_raw[];
+  const VfhConst& c = v.c;
+  const int H = c.hist_size, W = c.window, nf = v.nf;
+  /* carve */
+  float* s_window = reinterpret_cast<float*>(vfh_smem_raw); /* 128B aligned, TMA destination (FROM_GRID only) */
+  size_t off = FROM_GRID ? (((size_t)ga.box_r * ga.box_c * sizeof(float) + 127) & ~(size_t)127) : 0;
+  double* s_ranges = reinterpret_cast<double*>(vfh_smem_raw + off);
+  off += sizeof(double) * (B200NAV_NRANGES + 1);
+  float* s_hist = reinterpret_cast<float*>(vfh_smem_raw + off);
+  off += sizeof(float) * ((H + 1) & ~1);
+  uint16_t* s_nz = reinterpret_cast<uint16_t*>(vfh_smem_raw + off);
+
+  __shared__ SubmapInfo s_sub;
+  __shared__ int s_sub_ok;
+  __shared__ int s_warp_cnt[2][B200NAV_VFH_THREADS / 32];
+  __shared__ float s_red[2][B200NAV_VFH_THREADS / 32];
+  __shared__ __align__(8) unsigned long long s_mbar;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int robot = robot0 + blockIdx.x;
+  const b200nav_vfh_input inp = in[blockIdx.x];
+  uint32_t flags = 0;
+
+  /* ================= stage R: pseudo-scan ================= */
+  if (FROM_GRID) {
+    const RobotGeom g = ga.geom[robot];
+    if (tid == 0) {
+      SubmapInfo si;
+      const bool ok = submap_info(ga.dims, g, inp.x, inp.y, c.submap_length, c.submap_length, si);
+      s_sub = si;
+      s_sub_ok = ok ? 1 : 0;
+      /* TMA path needs a window that does not cross the circular-buffer seam */
+      int tma = ga.use_tma && ok && si.size_r <= ga.box_r && si.size_c <= ga.box_c &&
+                si.tl_r + si.size_r <= ga.dims.rows && si.tl_c + si.size_c <= ga.dims.cols;
+      s_sub_ok |= tma ? 2 : 0;
+      if (tma) {
+        const uint32_t mbar = smem_u32(&s_mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)(ga.box_r * ga.box_c * sizeof(float));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(s_window)), "l"(&tmap), "r"(si.tl_r), "r"(si.tl_c), "r"(robot), "r"(mbar)
+            : "memory");
+      }
+    }
+    for (int i = tid; i < B200NAV_NRANGES; i += blockDim.x) s_ranges[i] = 5000.0;
+    __syncthreads();
+    const int sub_ok = s_sub_ok;
+    if (sub_ok & 1) {
+      const SubmapInfo si = s_sub;
+      const bool tma = (sub_ok & 2) != 0;
+      if (tma) { /* wait for the window */
+        const uint32_t mbar = smem_u32(&s_mbar);
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile(
+              "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+              : "=r"(done)
+              : "r"(mbar), "r"(0)
+              : "memory");
+        }
+      }
+      const float* lay = ga.layer + (size_t)robot * ga.dims.rows * ga.dims.cols;
+      const int ncell = si.size_r * si.size_c;
+      const double res = ga.dims.res;
+      const double offx = si.pos_x + (0.5 * si.len_x - 0.5 * res), offy = si.pos_y + (0.5 * si.len_y - 0.5 * res);
+      for (int lin = tid; lin < ncell; lin += blockDim.x) {
+        const int i0 = lin % si.size_r, i1 = lin / si.size_r;
+        float value;
+        if (tma) {
+          value = s_window[i1 * ga.box_r + i0];
+        } else {
+          int b0 = si.utl_r + i0, b1 = si.utl_c + i1;
+          if ((g.start0 | g.start1) != 0) {
+            b0 += g.start0;
+            b1 += g.start1;
+            wrap_index(b0, ga.dims.rows);
+            wrap_index(b1, ga.dims.cols);
+          }
+          value = lay[(size_t)b1 * ga.dims.rows + b0];
+        }
+        if (isnan(value) || value <= c.occupied_threshold) continue;
+        const double px = offx + res * (double)(-i0), py = offy + res * (double)(-i1);
+        const double angle = atan2(py - inp.y, px - inp.x);
+        const double a = angle - inp.yaw + 3.14 / 2;
+        const double twopi = 2.0 * 3.14159265358979323846;
+        const double np = fmod(fmod(a, twopi) + twopi, twopi);
+        const double deg = np * 180.0 / 3.14159265358979323846;
+        if (!(deg <= 180)) continue; /* also rejects NaN poses */
+        const int fl = (int)floor(deg), ce = (int)ceil(deg);
+        const double dx = inp.x - px, dy = inp.y - py;
+        const double distance = sqrt(dx * dx + dy * dy) * 1000.0;
+        atomic_min_pos_double(&s_ranges[fl * 2], distance);
+        atomic_min_pos_double(&s_ranges[ce * 2], distance);
+      }
+    } else {
+      flags |= B200NAV_CMD_NO_SUBMAP;
+    }
+    __syncthreads();
+    for (int i = tid; i < B200NAV_NRANGES; i += blockDim.x) v.ranges[(size_t)robot * B200NAV_NRANGES + i] = s_ranges[i];
+  } else {
+    for (int i = tid; i < B200NAV_NRANGES; i += blockDim.x) {
+      const double r = dev_ranges[(size_t)blockIdx.x * 2 * B200NAV_NRANGES + 2 * i];
+      s_ranges[i] = r;
+      v.ranges[(size_t)robot * B200NAV_NRANGES + i] = r;
+    }
+    __syncthreads();
+  }
+
+  /* ================= Update_VFH prologue (vfh.cpp:491-515) ================= */
+  VfhRobotState st = v.st[robot];
+  st.desired = inp.goal_direction;
+  int speed = inp.current_speed < 0 ? 0 : inp.current_speed;
+  if (speed < st.last_chosen_speed) speed = st.last_chosen_speed;
+
+  /* ================= stage M: cell magnitudes -> ordered list of occupied cells ================= */
+  const float r_safe = c.robot_radius + (float)vfh_safety_dist(c, speed);
+  int nz_count = 0;
+  int emergency_local = 0;
+  for (int f0 = 0, it = 0; f0 < nf; f0 += blockDim.x, it++) {
+    const int f = f0 + tid;
+    bool occ = false;
+    if (f < nf) {
+      const int k = v.kidx[f];
+      if (k >= 0 && v.thr[f] > s_ranges[k]) {
+        const int x = f % W, y = f / W;
+        if (v.dist[f] < r_safe && !(x == c.center && y == c.center)) emergency_local = 1;
+        occ = true;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) s_warp_cnt[it & 1][warp] = __popc(bal);
+    __syncthreads();
+    int pos = nz_count, tot = 0;
+#pragma unroll
+    for (int w = 0; w < B200NAV_VFH_THREADS / 32; w++) {
+      const int cw = s_warp_cnt[it & 1][w];
+      if (w < warp) pos += cw;
+      tot += cw;
+    }
+    if (occ) s_nz[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)f;
+    nz_count += tot;
+  }
+  const int emergency = __syncthreads_or(emergency_local);
+
+  float* g_origin = v.origin_hist + (size_t)robot * H;
+  float* g_hist = v.hist + (size_t)robot * H;
+  float* g_last = v.last_binary + (size_t)robot * H;
+
+  float phi_right = 0.f, phi_left = 180.f;
+  if (emergency) {
+    /* vfh.cpp:1070-1077: OriginHist all 1; Hist untouched */
+    for (int s = tid; s < H; s += blockDim.x) g_origin[s] = 1.0f;
+    flags |= B200NAV_CMD_EMERGENCY;
+  } else {
+    /* ================= stage H + B ================= */
+    const int tab = vfh_speed_index(c, speed);
+    const uint32_t* masks = v.masks + (size_t)tab * nf * c.nwords;
+    const float high = vfh_bin_high(c, speed), low = vfh_bin_low(c, speed);
+    for (int s = tid; s < H; s += blockDim.x) {
+      float h = 0.f;
+      const int word = s >> 5;
+      const uint32_t bit = 1u << (s & 31);
+      for (int j = 0; j < nz_count; j++) {
+        const int f = s_nz[j];
+        if (__ldg(&masks[(size_t)f * c.nwords + word]) & bit) h += __ldg(&v.base[f]);
+      }
+      g_origin[s] = h;
+      float b;
+      if (h > high) b = 1.0f;
+      else if (h < low) b = 0.0f;
+      else b = g_last[s];
+      g_last[s] = b;
+      s_hist[s] = b;
+    }
+    /* ================= stage K: blocked circles -> phi_right / phi_left ================= */
+    int mtr_idx = speed;
+    if (mtr_idx > c.current_max_speed) mtr_idx = c.current_max_speed; /* reference reads out of bounds here (H4c) */
+    const int mtr = v.mtr[mtr_idx];
+    const float cxr = c.center + (mtr / (float)c.cell_width);
+    const float cxl = c.center - (mtr / (float)c.cell_width);
+    const float cy = c.center;
+    const float rb = mtr + c.robot_radius + vfh_safety_dist(c, speed);
+    st.blocked_radius = rb;
+    float pr = 0.f, pl = 180.f;
+    for (int j = tid; j < nz_count; j += blockDim.x) {
+      const int f = s_nz[j];
+      const float d = v.dir[f];
+      const int x = f % W, y = f / W;
+      if (vfh_delta_angle(d, 90.f) > 0) {
+        const float dist_r = vfh_hypotf(cxr - x, cy - y) * c.cell_width;
+        if (dist_r < rb) pr = fmaxf(pr, d);
+      } else {
+        const float dist_l = vfh_hypotf(cxl - x, cy - y) * c.cell_width;
+        if (dist_l < rb) pl = fminf(pl, d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pr = fmaxf(pr, __shfl_xor_sync(0xffffffffu, pr, o));
+      pl = fminf(pl, __shfl_xor_sync(0xffffffffu, pl, o));
+    }
+    if (lane == 0) {
+      s_red[0][warp] = pr;
+      s_red[1][warp] = pl;
+    }
+    __syncthreads(); /* also publishes s_hist */
+#pragma unroll
+    for (int w = 0; w < B200NAV_VFH_THREADS / 32; w++) {
+      phi_right = fmaxf(phi_right, s_red[0][w]);
+      phi_left = fminf(phi_left, s_red[1][w]);
+    }
+    /* mask (vfh.cpp:1196-1210) */
+    for (int s = tid; s < H; s += blockDim.x) {
+      const float angle = (float)(s * c.sector_angle);
+      float m;
+      if ((s_hist[s] == 0) &&
+          (((vfh_delta_angle(angle, phi_right) <= 0) && (vfh_delta_angle(angle, 90.f) >= 0)) ||
+           ((vfh_delta_angle(angle, phi_left) >= 0) && (vfh_delta_angle(angle, 90.f) <= 0))))
+        m = 0.f;
+      else
+        m = 1.f;
+      s_hist[s] = m;
+      g_hist[s] = m;
+    }
+    __syncthreads();
+  }
+
+  /* ================= stage S: direction, speed, turn rate (single thread) ================= */
+  if (tid == 0) {
+    if (emergency) {
+      st.picked = st.last_picked;
+      st.max_speed_for_picked = 0;
+      st.last_picked = st.picked;
+    } else {
+      int start = -1;
+      for (int i = 0; i < H / 2; i++)
+        if (s_hist[i] == 1) {
+          start = i;
+          break;
+        }
+      if (start == -1) {
+        st.picked = st.desired;
+        st.last_picked = st.picked;
+        st.max_speed_for_picked = c.current_max_speed;
+      } else {
+        /* openings -> candidates -> first minimum of the weight (vfh.cpp:786-868, 715-749) */
+        int n_cand = 0;
+        float best_angle = 90.f, min_weight = 10000000.f;
+        int best_speed = st.max_speed_for_picked;
+        auto consider = [&](float cand, int cand_speed) {
+          const float weight = c.u1 * fabsf(vfh_delta_angle(st.desired, cand)) +
+                               c.u2 * fabsf(vfh_delta_angle(st.last_picked, cand));
+          if (weight < min_weight) {
+            min_weight = weight;
+            best_angle = cand;
+            best_speed = cand_speed;
+          }
+          n_cand++;
+        };
+        const int cmax = c.current_max_speed;
+        const int sp_narrow = (cmax < c.max_speed_narrow) ? cmax : c.max_speed_narrow;
+        const int sp_wide = (cmax < c.max_speed_wide) ? cmax : c.max_speed_wide;
+        int left = 1, first = 0, second = 0;
+        for (int i = start; i <= start + H; i++) {
+          const int s = i % H;
+          if ((s_hist[s] == 0) && left) {
+            first = s * c.sector_angle;
+            left = 0;
+          }
+          if ((s_hist[s] == 1) && !left) {
+            second = (s - 1) * c.sector_angle;
+            if (second < 0) second += 360;
+            left = 1;
+            const float angle = vfh_delta_angle((float)first, (float)second);
+            if (fabsf(angle) < 10) continue;
+            const float centre = (float)(first + (second - first) / 2.0);
+            if (fabsf(angle) < 80) {
+              consider(centre, sp_narrow);
+            } else {
+              consider(centre, cmax);
+              const float c2 = (float)((first + 40) % 360);
+              consider(c2, sp_wide);
+              float c3 = (float)(second - 40);
+              if (c3 < 0) c3 += 360;
+              consider(c3, sp_wide);
+              if ((vfh_delta_angle(st.desired, c2) < 0) && (vfh_delta_angle(st.desired, c3) > 0))
+                consider(st.desired, sp_wide);
+            }
+          }
+        }
+        if (n_cand == 0) {
+          st.picked = st.last_picked;
+          st.max_speed_for_picked = 0;
+          st.last_picked = st.picked;
+          flags |= B200NAV_CMD_HEMMED_IN;
+        } else {
+          st.picked = best_angle;
+          st.max_speed_for_picked = best_speed;
+          st.last_picked = st.picked;
+        }
+      }
+    }
+    /* speed (vfh.cpp:566-599) */
+    int speed_incr;
+    if ((inp.dt > 0.3) || (inp.dt < 0)) speed_incr = 10;
+    else speed_incr = (int)(c.max_acceleration * inp.dt);
+    {
+      /* Cant_Turn_To_Goal (vfh.cpp:612-654) */
+      const float goal_x = (float)(inp.goal_distance * cos((st.desired) * 3.14159265358979323846 / 180));
+      const float goal_y = (float)(inp.goal_distance * sin((st.desired) * 3.14159265358979323846 / 180));
+      const float rb = st.blocked_radius;
+      bool cant = false;
+      float dc = vfh_hypotf(goal_x - rb, goal_y);
+      if (dc + inp.goal_tolerance < rb) cant = true;
+      if (!cant) {
+        dc = vfh_hypotf(-goal_x - rb, goal_y);
+        if (dc + inp.goal_tolerance < rb) cant = true;
+      }
+      if (cant) {
+        speed_incr = -speed_incr;
+        flags |= B200NAV_CMD_CANT_TURN;
+      }
+    }
+    int chosen_speed = st.last_chosen_speed + speed_incr;
+    if (!(chosen_speed < st.max_speed_for_picked)) chosen_speed = st.max_speed_for_picked;
+    /* Set_Motion (vfh.cpp:1222-1261) */
+    int turnrate;
+    const int mt = vfh_max_turnrate(c, speed);
+    if (chosen_speed <= 0) {
+      turnrate = mt;
+      chosen_speed = 0;
+    } else {
+      if ((st.picked > 270) && (st.picked < 360)) {
+        turnrate = -1 * mt;
+      } else if ((st.picked < 270) && (st.picked > 180)) {
+        turnrate = mt;
+      } else {
+        turnrate = (int)rint(((float)(st.picked - 90) / 75.0) * mt);
+        if (turnrate > mt) turnrate = mt;
+        else if (turnrate < (-1 * mt)) turnrate = -1 * mt;
+      }
+    }
+    st.last_chosen_speed = chosen_speed;
+    v.st[robot] = st;
+    b200nav_command cmd;
+    cmd.speed = chosen_speed;
+    cmd.turnrate = turnrate;
+    cmd.picked_angle = st.picked;
+    cmd.flags = flags;
+    out[blockIdx.x] = cmd;
+  }
+}
+
+}  // namespace b200nav
+#endif
