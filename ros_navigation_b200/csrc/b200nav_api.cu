@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -226,11 +227,12 @@ PFN_tmapEncodeTiled get_encode_fn() {
 void vfh_window_box(const b200nav_vfh* v, const b200nav_grid* g, int& box_r, int& box_c) {
   const int n = (int)ceil(v->tab.c.submap_length / g->dims.res) + 2;
   box_c = std::min(n, g->dims.cols);
-  box_r = std::min((n + 3) & ~3, (g->dims.rows + 3) & ~3);
+  box_r = std::min((n + 3 + 3) & ~3, (g->dims.rows + 3) & ~3); /* +3: the box starts at a 4-float aligned row */
 }
 
 bool vfh_prepare_tmap(b200nav_vfh* v, b200nav_grid* g, const float* layer, int box_r, int box_c) {
-  if (v->tma_disabled) return false;
+  static const bool env_off = getenv("B200NAV_DISABLE_TMA") != nullptr; /* debugging aid */
+  if (v->tma_disabled || env_off) return false;
   if (g->dims.rows % 4 != 0 || box_r > 256 || box_c > 256) return false;
   if (v->tmap_valid && v->tmap_layer == layer && v->tmap_rows == g->dims.rows && v->tmap_cols == g->dims.cols &&
       v->tmap_robots == g->n_robots && v->tmap_box_r == box_r && v->tmap_box_c == box_c)

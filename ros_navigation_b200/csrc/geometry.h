@@ -139,10 +139,11 @@ B200_HD BeamSeg make_beam(const GridDims& d, const RobotGeom& g, double sx, doub
   BeamSeg b;
   b.r0 = b.c0 = b.r1 = b.c1 = -1;
   b.mr = b.mc = -1;
+  /* Non-finite coordinates would make the reference's clip loop spin forever; defined as "no line".  The mark
+   * only depends on the end point (map_updater.h:44-49). */
   const bool finite = isfinite(sx) && isfinite(sy) && isfinite(ex) && isfinite(ey);
-  if (!finite) return b;
   int r0, c0, r1, c1;
-  if (clip_into_map(d, g, sx, sy, ex, ey, r0, c0) && clip_into_map(d, g, ex, ey, sx, sy, r1, c1)) {
+  if (finite && clip_into_map(d, g, sx, sy, ex, ey, r0, c0) && clip_into_map(d, g, ex, ey, sx, sy, r1, c1)) {
     b.r0 = r0;
     b.c0 = c0;
     b.r1 = r1;

@@ -144,7 +144,9 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
       s_sub = si;
       s_sub_ok = ok ? 1 : 0;
       /* TMA path needs a window that does not cross the circular-buffer seam */
-      int tma = ga.use_tma && ok && si.size_r <= ga.box_r && si.size_c <= ga.box_c &&
+      /* TMA (tiled, no interleave) needs the innermost coordinate 16-byte aligned: start the box at row
+       * tl_r & ~3 and skip the first (tl_r & 3) floats of every staged column. */
+      int tma = ga.use_tma && ok && si.size_r + (si.tl_r & 3) <= ga.box_r && si.size_c <= ga.box_c &&
                 si.tl_r + si.size_r <= ga.dims.rows && si.tl_c + si.size_c <= ga.dims.cols;
       s_sub_ok |= tma ? 2 : 0;
       if (tma) {
@@ -155,7 +157,7 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_u32(s_window)), "l"(&tmap), "r"(si.tl_r), "r"(si.tl_c), "r"(robot), "r"(mbar)
+            ::"r"(smem_u32(s_window)), "l"(&tmap), "r"(si.tl_r & ~3), "r"(si.tl_c), "r"(robot), "r"(mbar)
             : "memory");
       }
     }
@@ -184,7 +186,7 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
         const int i0 = lin % si.size_r, i1 = lin / si.size_r;
         float value;
         if (tma) {
-          value = s_window[i1 * ga.box_r + i0];
+          value = s_window[i1 * ga.box_r + i0 + (si.tl_r & 3)];
         } else {
           int b0 = si.utl_r + i0, b1 = si.utl_c + i1;
           if ((g.start0 | g.start1) != 0) {

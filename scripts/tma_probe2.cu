@@ -1,0 +1,68 @@
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void k(const __grid_constant__ CUtensorMap tm, const CUtensorMap* gtm, int mode, int r, int c, float* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  float* win = (float*)smem;
+  const int box_elems = 32 * 32;
+  unsigned mb = s32(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(box_elems * 4) : "memory");
+    unsigned long long desc = (mode == 1) ? (unsigned long long)gtm : (unsigned long long)&tm;
+    if (mode == 2)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                   ::"r"(s32(win)), "l"(desc), "r"(r), "r"(c), "r"(mb) : "memory");
+    else
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                   ::"r"(s32(win)), "l"(desc), "r"(r), "r"(c), "r"(mb) : "memory");
+  }
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(mb), "r"(0) : "memory");
+  for (int i = threadIdx.x; i < box_elems; i += blockDim.x) out[i] = win[i];
+}
+
+int main(int argc, char** argv) {
+  const int mode = argc > 1 ? atoi(argv[1]) : 0;
+  CUresult ir = CUDA_SUCCESS;
+  void* p = nullptr; cudaDriverEntryPointQueryResult q;
+  cudaFree(0);
+  cudaError_t ge = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  printf("mode %d entry: %s q=%d p=%p\n", mode, cudaGetErrorString(ge), (int)q, p);
+  PFN enc = (PFN)p;
+  const int rows = argc > 2 ? atoi(argv[2]) : 256, cols = 200; const int r0 = argc > 3 ? atoi(argv[3]) : 64;
+  std::vector<float> h((size_t)rows * cols);
+  for (size_t i = 0; i < h.size(); i++) h[i] = (float)i;
+  float *d, *out; cudaMalloc(&d, h.size() * 4); cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+  cudaMalloc(&out, 64 * 64 * 4);
+  alignas(64) CUtensorMap tm; memset(&tm, 0, sizeof(tm));
+  cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)cols}; cuuint64_t gstr[1] = {(cuuint64_t)rows * 4};
+  cuuint32_t box[2] = {32, 32}; cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  printf("encode rc=%d\n", (int)r);
+  const unsigned long long* w = (const unsigned long long*)&tm;
+  for (int i = 0; i < 16; i++) printf("%016llx%s", w[i], (i % 4 == 3) ? "\n" : " ");
+  CUtensorMap* gtm; cudaMalloc(&gtm, sizeof(tm)); cudaMemcpy(gtm, &tm, sizeof(tm), cudaMemcpyHostToDevice);
+  k<<<1, 128, 32 * 32 * 4 + 1024>>>(tm, gtm, mode, r0, 90, out);
+  cudaError_t e = cudaDeviceSynchronize();
+  float o[4] = {0}; if (!e) cudaMemcpy(o, out, 16, cudaMemcpyDeviceToHost);
+  printf("  run: %s  out[0..1]=%g %g (expect %d %d)\n", cudaGetErrorString(e), o[0], o[1], 90 * rows + r0, 90 * rows + r0 + 1);
+  (void)ir;
+  return e ? 1 : 0;
+}
