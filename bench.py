@@ -1,0 +1,492 @@
+#!/usr/bin/env python
+"""bench.py -- laser scans/sec fused into the HIMM grid + VFH+ steering decisions/sec (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c4] [--impl reference]
+
+A step = one cycle of the batched perception-to-steering path: every robot fuses ONE laser scan into its HIMM grid
+(b200nav_himm_update_batched*) and takes ONE VFH+ decision from the window of that grid
+(b200nav_vfh_update_batched*); with N > 1 ranks the per-robot 16-byte steering commands are all-gathered (NCCL).
+Default workload = BASELINE config 4 ("batched 1024 independent robots, each a 512x512 grid and 1080-beam scans,
+sharded across 1/2/4/8 B200"): the 1024 robots are block-partitioned over the ranks (strong scaling, no data-path
+collective).  Inputs are synthetic (ros_navigation_b200/synth.py), pre-staged in HBM for `value` and in pinned host
+memory for `e2e`.  L2 is flushed between timed steps; every step is timed with CUDA events on the launching stream.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "laser scans/sec fused into HIMM grid + VFH+ steering decisions/sec"
+UNIT = "scans/s (each scan = 1 HIMM grid update + 1 VFH+ decision)"
+N_CYCLES = 8          # distinct pre-generated cycles replayed round-robin (inputs > L2 at N=1)
+L2_FLUSH_BYTES = 256 << 20
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload construction (shared by both arms)
+# ----------------------------------------------------------------------------------------------------------------
+def local_robot_range(total, rank, world):
+    per = total // world
+    rem = total % world
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+class Cycles:
+    """Pre-generated scan cycles for the robots [lo, hi) of a config."""
+
+    def __init__(self, cfg_name, lo, hi, device, n_cycles=N_CYCLES):
+        import torch
+        from ros_navigation_b200 import synth
+        self.cfg = cfg = synth.CONFIGS[cfg_name]
+        self.n = hi - lo
+        self.device = device
+        seed = synth.config_seed(cfg_name, rank=lo)
+        self.worlds = synth.Worlds(self.n, cfg["extent"], seed, device=device)
+        dt = 1.0 / cfg["rate"]
+        self.dt = dt
+        self.samples, self.offsets, self.inputs, self.totals = [], [], [], []
+        for c in range(n_cycles):
+            t = c * dt * 5  # spread the replayed poses a little so cycles are distinct
+            x, y, yaw = self.worlds.pose(t)
+            r, ang = self.worlds.cast(x, y, yaw, cfg["beams"], cfg["fov"], cfg["range_max"])
+            s8, off = synth.samples_from_scan(x, y, yaw, r, ang, cfg["range_max"])
+            self.samples.append(s8.contiguous())
+            self.offsets.append(off.contiguous())
+            self.totals.append(int(off[-1]))
+            self.inputs.append(synth.vfh_inputs(self.worlds, t, dt, 150).contiguous())
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            sm_sorted = sorted(sm)
+            out.update(sm_mhz=sm_sorted[len(sm_sorted) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU algorithm on the host cores (oracle restatement + reference vfh.cpp)
+# ----------------------------------------------------------------------------------------------------------------
+class CpuArm:
+    """HIMM + pseudo-scan restatement (oracle/himm_oracle.cpp) and the reference VFH class (oracle/_ref) for a
+    bounded sample of robots, one Python thread per host core (the C calls release the GIL)."""
+
+    def __init__(self, cfg_name, n_robots, n_cycles=4):
+        import numpy as np
+        import torch
+        from oracle import oracle as O
+        from ros_navigation_b200 import synth
+        self.O, self.np = O, np
+        self.cores = max(1, os.cpu_count() or 1)
+        self.n = n_robots
+        cyc = Cycles(cfg_name, 0, n_robots, torch.device("cpu"), n_cycles=n_cycles)
+        self.cfg = cfg = cyc.cfg
+        self.geom = O.make_geom(cfg["extent"], cfg["extent"], cfg["res"])
+        self.layers = [O.new_layer(self.geom) for _ in range(n_robots)]
+        self.kind = "port+reference" if O.have_ref() else "port"
+        self.vfh = None
+        if O.have_ref():
+            self.vfh = [O.RefVFH(window_diameter=cfg["window"], cell_size=cfg["cell"]) for _ in range(n_robots)]
+        self.samples = [synth.samples_to_numpy(s) for s in cyc.samples]
+        self.offsets = [o.numpy() for o in cyc.offsets]
+        self.inputs = [synth.vfh_inputs_to_numpy(i) for i in cyc.inputs]
+        self.n_cycles = n_cycles
+        self.submap = cfg["submap"]
+
+    def _robot_cycle(self, r, c):
+        O = self.O
+        off = self.offsets[c]
+        O.himm_update(self.geom, self.layers[r], self.samples[c][off[r]:off[r + 1]])
+        inp = self.inputs[c][r]
+        # master := laser is aliased on the GPU side; the reference copies the layer (map_provider.cpp:221) - the
+        # copy is excluded on both sides.
+        rng = O.ranges_from_submap(self.geom, self.layers[r], float(inp["x"]), float(inp["y"]), float(inp["yaw"]),
+                                   self.submap)
+        if self.vfh is not None:
+            self.vfh[r].update(rng, int(inp["current_speed"]), float(inp["goal_direction"]),
+                               float(inp["goal_distance"]), float(inp["goal_tolerance"]), float(inp["dt"]))
+
+    def run_cycle(self, c):
+        """One cycle over all sample robots on all cores; returns seconds."""
+        c = c % self.n_cycles
+        chunks = [list(range(i, self.n, self.cores)) for i in range(self.cores)]
+
+        def work(rs):
+            for r in rs:
+                self._robot_cycle(r, c)
+
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=work, args=(rs,)) for rs in chunks if rs]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0
+
+
+def cpu_sample_size(cfg_name):
+    # ~0.3-3 s of CPU work per cycle on 8-32 cores
+    return {"c1": 64, "c2": 16, "c3": 8, "c4": 256, "c5": 512}.get(cfg_name, 64)
+
+
+def run_reference_arm(args, rank, world):
+    """bench.py --impl reference: the CPU implementation on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    arm = CpuArm(args.workload, cpu_sample_size(args.workload))
+    for w in range(args.warmup):
+        arm.run_cycle(w)
+    secs = 0.0
+    for k in range(args.steps):
+        secs += arm.run_cycle(args.warmup + k)
+    value = arm.n * args.steps / secs
+    sample = "%d robots x %d cycles of workload %s per run" % (arm.n, args.steps, args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 cells / f64 geometry", "data": "synthetic",
+        "config": workload_config(args.workload, world, args.robots or arm.cfg["robots"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, world, robots_total):
+    from ros_navigation_b200 import synth
+    cfg = synth.CONFIGS[name]
+    rows = int(round(cfg["extent"] / cfg["res"]))
+    return {
+        "workload": "%s: %d robots x %dx%d grid @%g m, %d-beam scans <= %g m, VFH+ 72 sectors window %d" % (
+            name, robots_total, rows, rows, cfg["res"], cfg["beams"], cfg["range_max"], cfg["window"]),
+        "robots": robots_total, "grid": [rows, rows], "beams": cfg["beams"], "parallelism": "robots/%d" % world,
+        "l2": "flushed between timed steps (256 MiB write); %d distinct cycles replayed" % N_CYCLES,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+class GpuArm:
+    def __init__(self, cfg_name, lo, hi, device, stream, world):
+        import torch
+        from ros_navigation_b200 import VFH, DeviceGridMap, VfhParams, capi
+        self.torch = torch
+        self.world = world
+        self.cyc = Cycles(cfg_name, lo, hi, device)
+        cfg = self.cfg = self.cyc.cfg
+        self.n = hi - lo
+        self.ctx = capi.Context(device.index, stream=stream.cuda_stream)
+        self.grid = DeviceGridMap(self.ctx, (cfg["extent"],) * 2, cfg["res"], n_robots=self.n, layers=("laser",))
+        self.grid.alias("master", "laser")  # map_["master"] = map_["laser"] without the copy
+        self.vfh = VFH(self.ctx, VfhParams(window_diameter=cfg["window"], cell_size=cfg["cell"],
+                                           submap_length=cfg["submap"]), n_robots=self.n)
+        self.cmd = torch.zeros(self.n, 16, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(world * self.n, 16, dtype=torch.uint8, device=device) if world > 1 else None
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+        # pinned host copies for the end-to-end path
+        self.h_samples = [s.cpu().pin_memory() for s in self.cyc.samples]
+        self.h_offsets = [o.cpu().pin_memory() for o in self.cyc.offsets]
+        self.h_inputs = [i.cpu().pin_memory() for i in self.cyc.inputs]
+        self.d_inputs_e2e = torch.zeros_like(self.cyc.inputs[0])
+        self.h_cmd = torch.zeros((world * self.n if world > 1 else self.n), 16, dtype=torch.uint8).pin_memory()
+
+    def all_gather(self):
+        if self.gathered is not None:
+            self.torch.distributed.all_gather_into_tensor(self.gathered.view(-1), self.cmd.view(-1))
+
+    def step_dev(self, i):
+        c = i % N_CYCLES
+        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c])
+        self.vfh.update_batched_dev(self.grid, "master", self.cyc.inputs[c], self.cmd)
+        self.all_gather()
+
+    def step_e2e(self, i):
+        """Host buffers in, host result out: H2D of samples/offsets/VFH inputs and D2H of the commands inside."""
+        c = i % N_CYCLES
+        from ros_navigation_b200.capi import check, lib
+        check(lib().b200nav_himm_update_batched(self.grid.h, b"laser", self.h_samples[c].data_ptr(),
+                                                self.h_offsets[c].data_ptr(), None), self.ctx.h)
+        self.d_inputs_e2e.copy_(self.h_inputs[c], non_blocking=True)
+        self.vfh.update_batched_dev(self.grid, "master", self.d_inputs_e2e, self.cmd)
+        self.all_gather()
+        src = self.gathered if self.gathered is not None else self.cmd
+        self.h_cmd.copy_(src, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+    def e2e_bytes(self, c):
+        h2d = self.h_samples[c].numel() + self.h_offsets[c].numel() * 4 + self.h_inputs[c].numel()
+        return h2d, self.h_cmd.numel()
+
+    def algorithmic_bytes(self, c):
+        """8 B per cell visit + 8 B per mark + 36 B per beam, for cycle c (this rank)."""
+        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c])
+        visits, marks, beams = self.grid.himm_last_stats()
+        return 8 * visits + 8 * marks + 36 * beams, visits, marks, beams
+
+
+def timed_steps(torch, stream, step_fn, first, n, flush):
+    """n steps, each bracketed by CUDA events on `stream`, L2 flushed before every step. Returns ms list."""
+    evs = []
+    for k in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        step_fn(first + k)
+        b.record(stream)
+        evs.append((a, b))
+    stream.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ros_navigation_b200 import synth
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    cfg = synth.CONFIGS[args.workload]
+    robots_total = args.robots or cfg["robots"]
+    lo, hi = local_robot_range(robots_total, rank, world)
+    stream = torch.cuda.Stream(device)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else \
+        (6650.0, "fallback (B200_PROFILING.md)")
+
+    with torch.cuda.stream(stream):
+        arm = GpuArm(args.workload, lo, hi, device, stream, world)
+        # algorithmic bytes per cycle (also warms every cycle once)
+        alg = [arm.algorithmic_bytes(c) for c in range(N_CYCLES)]
+        for w in range(args.warmup):
+            arm.step_dev(w)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        arm.ctx.profile_enable(True)
+        launches0 = arm.ctx.launches
+        t_wall0 = time.perf_counter()
+        ms = timed_steps(torch, stream, arm.step_dev, args.warmup, args.steps, arm.flush)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t_wall0
+        launches = arm.ctx.launches - launches0
+        tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
+        prep_ms, prep_n = arm.ctx.profile_read("himm_prep")
+        vfh_ms, vfh_n = arm.ctx.profile_read("vfh_update")
+        arm.ctx.profile_enable(False)
+        # ---- end-to-end: host buffers through the C ABI ----
+        for w in range(max(3, args.warmup // 2)):
+            arm.step_e2e(w)
+        if world > 1:
+            dist.barrier()
+        e2e_s = 0.0
+        for k in range(args.steps):
+            arm.flush.zero_()
+            stream.synchronize()
+            t0 = time.perf_counter()
+            arm.step_e2e(args.warmup + k)
+            e2e_s += time.perf_counter() - t0
+        clk = clocks.stop() if rank == 0 else None
+
+    total_ms = float(sum(ms))
+    t = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    value = robots_total * args.steps / (total_ms / 1000.0)
+    e2e_value = robots_total * args.steps / (e2e_ms / 1000.0)
+
+    if rank != 0:
+        return
+    # roofline of the dominant kernel (himm_tile_kernel), this rank's launches
+    used = [alg[(args.warmup + k) % N_CYCLES] for k in range(args.steps)]
+    alg_bytes = float(np.mean([u[0] for u in used]))
+    tile_avg_ms = tile_ms / max(tile_n, 1)
+    achieved = alg_bytes / (tile_avg_ms / 1000.0) / 1e9
+    h2d, d2h = arm.e2e_bytes(0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 cells / f64 geometry", "data": "synthetic",
+        "config": workload_config(args.workload, world, robots_total),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "himm_tile_kernel", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "avg_launch_ms": tile_avg_ms, "launches_timed": int(tile_n),
+                     "visits_per_launch": float(np.mean([u[1] for u in used]))},
+        "kernel_ms_per_step": {"himm_prep": prep_ms / max(prep_n, 1), "himm_tile": tile_avg_ms,
+                               "vfh_update": vfh_ms / max(vfh_n, 1)},
+        "wall_s_timed_region": wall,
+    }
+    # ---- CPU baseline on a bounded sample (rank 0, N == 1 only) ----
+    if world == 1 and not args.no_cpu:
+        try:
+            cpu = CpuArm(args.workload, cpu_sample_size(args.workload))
+            t_cal = cpu.run_cycle(0)
+            n_cyc = int(max(2, min(40, 12.0 / max(t_cal, 1e-3))))
+            secs = sum(cpu.run_cycle(1 + k) for k in range(n_cyc))
+            line["cpu_baseline"] = {"value": cpu.n * n_cyc / secs, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
+                                    "sample": "%d robots x %d cycles of workload %s (%.1f s)" % (
+                                        cpu.n, n_cyc, args.workload, secs)}
+        except Exception as e:  # the baseline must never take the GPU number down
+            line["cpu_baseline"] = {"error": repr(e)}
+    if world == 1 and args.workload == "c4" and not args.no_extra:
+        try:
+            line["other_workloads"] = {"c2": single_robot_numbers(device, "c2")}
+        except Exception as e:
+            line["other_workloads"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+
+
+def single_robot_numbers(device, name, scans=300):
+    """BASELINE config 2: one robot, 2048x2048 grid, 1080-beam scans replayed back to back (latency bound)."""
+    import torch
+    stream = torch.cuda.Stream(device)
+    with torch.cuda.stream(stream):
+        arm = GpuArm(name, 0, 1, device, stream, 1)
+        for w in range(10):
+            arm.step_dev(w)
+        stream.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for k in range(scans):
+            arm.step_dev(k)
+        b.record(stream)
+        stream.synchronize()
+        dev_ms = a.elapsed_time(b)
+        for w in range(5):
+            arm.step_e2e(w)
+        t0 = time.perf_counter()
+        for k in range(scans):
+            arm.step_e2e(k)
+        e2e_s = time.perf_counter() - t0
+    return {"workload": workload_config(name, 1, 1)["workload"], "value": scans / (dev_ms / 1000.0),
+            "e2e": scans / e2e_s, "unit": UNIT, "ms_per_scan": dev_ms / scans, "l2": "grid (16 MiB) L2-resident"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--robots", type=int, default=0, help="override the config's robot count")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip other_workloads")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the b200nav path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_gpu_arm(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

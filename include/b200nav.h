@@ -59,6 +59,12 @@ void* b200nav_ctx_stream(b200nav_ctx* ctx);
 const char* b200nav_last_error(b200nav_ctx* ctx);
 /* Number of kernels this context launched since creation (bench.py's gpu_launches). */
 int64_t b200nav_ctx_launch_count(b200nav_ctx* ctx);
+/* Per-kernel device timing with CUDA events on the context's stream (observability; the reference has only a
+ * loop-overrun warning, map_provider.cpp:170-173).  enable != 0 starts recording and resets the counters.
+ * b200nav_ctx_profile_read synchronises the stream and returns, for kernel `name` ("himm_prep", "himm_tile",
+ * "vfh_update"), the summed device time in milliseconds and the number of timed launches. */
+int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable);
+int b200nav_ctx_profile_read(b200nav_ctx* ctx, const char* name, double* total_ms, int64_t* launches);
 
 /* ------------------------------------------------------------------------------------------------------
  * Grid: device-resident grid_map::GridMap layers for n_robots independent maps of identical size.
@@ -123,6 +129,11 @@ int b200nav_himm_update_batched(b200nav_grid* grid, const char* layer, const b20
 /* Same with samples/offsets already in device memory; asynchronous (no stream sync).  total = offsets[n_robots]. */
 int b200nav_himm_update_batched_dev(b200nav_grid* grid, const char* layer, const b200nav_sample* dev_samples,
                                     const int32_t* dev_offsets, int total);
+
+/* Work statistics of the LAST himm update of this grid (all robots of that call): out[0] = cell visits
+ * (sum over beams of the Bresenham cell count), out[1] = marks, out[2] = beams.  Used for the algorithmic-byte
+ * accounting of the roofline (8 B per visit + 8 B per mark + 36 B per beam). */
+int b200nav_himm_last_stats(b200nav_grid* grid, int64_t* out3);
 
 /* ------------------------------------------------------------------------------------------------------
  * VFH+.  Replaces move_control::VFH (move_control/include/move_control/vfh.h:182-361,

@@ -46,6 +46,9 @@ _SIGNATURES = {
     "b200nav_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "b200nav_last_error": (C.c_char_p, [C.c_void_p]),
     "b200nav_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "b200nav_ctx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200nav_ctx_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "b200nav_himm_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200nav_grid_create": (C.c_int, [C.c_void_p] + [C.c_double] * 5 + [C.c_int, C.POINTER(C.c_void_p)]),
     "b200nav_grid_destroy": (C.c_int, [C.c_void_p]),
     "b200nav_grid_size": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 3),
@@ -152,6 +155,15 @@ class Context:
     @property
     def launches(self):
         return int(lib().b200nav_ctx_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        check(lib().b200nav_ctx_profile_enable(self.h, int(on)), self.h)
+
+    def profile_read(self, name):
+        """(total device ms, timed launches) of kernel `name` since profile_enable(True)."""
+        ms, n = C.c_double(), C.c_int64()
+        check(lib().b200nav_ctx_profile_read(self.h, name.encode(), C.byref(ms), C.byref(n)), self.h)
+        return ms.value, n.value
 
     def close(self):
         if self.h:

@@ -31,12 +31,24 @@ using namespace b200nav;
  * Objects
  * ============================================================================================================== */
 
+/* Event-pair pool for per-kernel device timing (b200nav_ctx_profile_*). */
+enum { PROF_HIMM_PREP = 0, PROF_HIMM_TILE = 1, PROF_VFH = 2, PROF_KINDS = 3 };
+static const char* const kProfNames[PROF_KINDS] = {"himm_prep", "himm_tile", "vfh_update"};
+struct ProfSlot {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs; /* recorded, not yet read */
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_pairs;
+  double total_ms = 0;
+  int64_t count = 0;
+};
+
 struct b200nav_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
   int64_t launches = 0;
   int sm_count = 0;
+  bool profiling = false;
+  ProfSlot prof[PROF_KINDS];
   char err[512] = {0};
 };
 
@@ -97,7 +109,8 @@ struct b200nav_grid {
   std::vector<RobotGeom> geom_host;
   RobotGeom* geom_dev = nullptr;
   std::map<std::string, Layer> layers;
-  DevBuf samples, segs, offsets, occ;
+  DevBuf samples, segs, offsets, occ, stats;
+  int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
 };
 
@@ -136,6 +149,45 @@ int check_launch(b200nav_ctx* ctx, const char* what) {
   return B200NAV_OK;
 }
 
+/* RAII-ish helper: record an event pair around a launch when profiling is on. */
+struct ProfScope {
+  b200nav_ctx* ctx;
+  int kind;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  ProfScope(b200nav_ctx* c, int k) : ctx(c), kind(k) {
+    if (!ctx->profiling) return;
+    ProfSlot& s = ctx->prof[kind];
+    if (!s.free_pairs.empty()) {
+      ev = s.free_pairs.back();
+      s.free_pairs.pop_back();
+    } else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) {
+      ev = {nullptr, nullptr};
+      return;
+    }
+    cudaEventRecord(ev.first, ctx->stream);
+  }
+  ~ProfScope() {
+    if (!ev.first) return;
+    cudaEventRecord(ev.second, ctx->stream);
+    ctx->prof[kind].pairs.push_back(ev);
+  }
+};
+
+void prof_drain(b200nav_ctx* ctx) {
+  for (int k = 0; k < PROF_KINDS; k++) {
+    ProfSlot& s = ctx->prof[k];
+    for (auto& p : s.pairs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) {
+        s.total_ms += ms;
+        s.count++;
+      }
+      s.free_pairs.push_back(p);
+    }
+    s.pairs.clear();
+  }
+}
+
 Layer* find_layer(b200nav_grid* g, const char* name) {
   if (!name) return nullptr;
   auto it = g->layers.find(name);
@@ -159,8 +211,8 @@ int upload_geom(b200nav_grid* g) {
 constexpr int kVfhMaxSmem = 200 * 1024;
 
 /* ---- HIMM launch ------------------------------------------------------------------------------------------- */
-constexpr int kSub = 64, kWR = 2, kWC = 2, kListCap = 2048;
-using TileCfg = HimmTileCfg<kSub, kWR, kWC, kListCap>;
+constexpr int kSub = 64, kListCap = 2048;
+using TileCfg = HimmTileCfg<kSub, kListCap>;
 
 int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
                 int robot0, int n_active, int single_n, int total) {
@@ -180,12 +232,19 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   a.total = total;
   a.tiles_r = (g->dims.rows + TileCfg::kTileR - 1) / TileCfg::kTileR;
   a.tiles_c = (g->dims.cols + TileCfg::kTileC - 1) / TileCfg::kTileC;
-  himm_prep_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(a);
+  g->last_total = total;
+  {
+    ProfScope ps(ctx, PROF_HIMM_PREP);
+    himm_prep_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(a);
+  }
   int rc = check_launch(ctx, "himm_prep_kernel");
   if (rc) return rc;
-  auto kern = himm_tile_kernel<kSub, kWR, kWC, kListCap>;
+  auto kern = himm_tile_kernel<kSub, kListCap>;
   dim3 grid((unsigned)(a.tiles_r * a.tiles_c), (unsigned)n_active);
-  kern<<<grid, TileCfg::kThreads, TileCfg::kSmemBytes, ctx->stream>>>(a);
+  {
+    ProfScope ps(ctx, PROF_HIMM_TILE);
+    kern<<<grid, TileCfg::kThreads, TileCfg::kSmemBytes, ctx->stream>>>(a);
+  }
   return check_launch(ctx, "himm_tile_kernel");
 }
 
@@ -287,10 +346,12 @@ int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const float* layer, const b200na
     smem = vfh_smem_bytes(v, true, box_r, box_c);
     if (smem > (size_t)kVfhMaxSmem) return set_err(ctx, B200NAV_ERANGE, "VFH window too large for shared memory (%zu B)", smem);
     auto kern = vfh_update_kernel<true>;
+    ProfScope ps(ctx, PROF_VFH);
     kern<<<n, B200NAV_VFH_THREADS, smem, ctx->stream>>>(v->dev, ga, tm, dev_in, nullptr, dev_out, robot0);
   } else {
     smem = vfh_smem_bytes(v, false, 0, 0);
     auto kern = vfh_update_kernel<false>;
+    ProfScope ps(ctx, PROF_VFH);
     kern<<<n, B200NAV_VFH_THREADS, smem, ctx->stream>>>(v->dev, ga, tm, dev_in, dev_ranges, dev_out, robot0);
   }
   return check_launch(ctx, "vfh_update_kernel");
@@ -298,7 +359,7 @@ int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const float* layer, const b200na
 
 /* Opt in to > 48 KB dynamic shared memory once per device (attributes are per device). */
 int configure_kernels(b200nav_ctx* ctx) {
-  CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_kernel<kSub, kWR, kWC, kListCap>,
+  CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_kernel<kSub, kListCap>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
   CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
   CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
@@ -359,6 +420,12 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
   if (!ctx) return B200NAV_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  prof_drain(ctx);
+  for (int k = 0; k < PROF_KINDS; k++)
+    for (auto& p : ctx->prof[k].free_pairs) {
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+    }
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200NAV_OK;
@@ -374,6 +441,32 @@ void* b200nav_ctx_stream(b200nav_ctx* ctx) { return ctx ? (void*)ctx->stream : n
 const char* b200nav_last_error(b200nav_ctx* ctx) { return ctx ? ctx->err : g_err; }
 
 int64_t b200nav_ctx_launch_count(b200nav_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable) {
+  if (!ctx) return B200NAV_EINVAL;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  prof_drain(ctx);
+  ctx->profiling = enable != 0;
+  if (enable)
+    for (int k = 0; k < PROF_KINDS; k++) {
+      ctx->prof[k].total_ms = 0;
+      ctx->prof[k].count = 0;
+    }
+  return B200NAV_OK;
+}
+
+int b200nav_ctx_profile_read(b200nav_ctx* ctx, const char* name, double* total_ms, int64_t* launches) {
+  if (!ctx || !name) return B200NAV_EINVAL;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  prof_drain(ctx);
+  for (int k = 0; k < PROF_KINDS; k++)
+    if (strcmp(name, kProfNames[k]) == 0) {
+      if (total_ms) *total_ms = ctx->prof[k].total_ms;
+      if (launches) *launches = ctx->prof[k].count;
+      return B200NAV_OK;
+    }
+  return set_err(ctx, B200NAV_EINVAL, "unknown kernel name '%s'", name);
+}
 
 /* ================================================================================================================
  * Grid
@@ -423,6 +516,7 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   g->segs.release();
   g->offsets.release();
   g->occ.release();
+  g->stats.release();
   delete g;
   return B200NAV_OK;
 }
@@ -680,6 +774,22 @@ int b200nav_himm_update_batched_dev(b200nav_grid* g, const char* layer, const b2
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
   return himm_launch(g, l->dev, dev_samples, dev_offsets, 0, g->n_robots, -1, total);
+}
+
+int b200nav_himm_last_stats(b200nav_grid* g, int64_t* out3) {
+  if (!g || !out3) return B200NAV_EINVAL;
+  b200nav_ctx* ctx = g->ctx;
+  out3[0] = out3[1] = out3[2] = 0;
+  if (g->last_total <= 0 || !g->segs.p) return B200NAV_OK;
+  CUDA_TRY(ctx, g->stats.reserve(3 * sizeof(unsigned long long)));
+  CUDA_TRY(ctx, cudaMemsetAsync(g->stats.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  const int blocks = std::min((g->last_total + 255) / 256, ctx->sm_count * 8);
+  himm_stats_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const BeamSeg*>(g->segs.p), g->last_total,
+                                                     static_cast<unsigned long long*>(g->stats.p));
+  int rc = check_launch(ctx, "himm_stats_kernel");
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out3, g->stats.p, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_stream(ctx);
 }
 
 /* ================================================================================================================

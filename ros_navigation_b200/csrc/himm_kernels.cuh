@@ -67,6 +67,27 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
   a.segs[i] = make_beam(a.dims, g, s.sx, s.sy, s.ex, s.ey, s.clear_end);
 }
 
+/* Work statistics over the BeamSegs of one update: cell visits, marks, beams (block reduce + 3 atomics per CTA). */
+__global__ void __launch_bounds__(256) himm_stats_kernel(const BeamSeg* __restrict__ segs, int total,
+                                                         unsigned long long* __restrict__ out3) {
+  unsigned long long visits = 0, marks = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const BeamSeg b = segs[i];
+    if (b.r0 >= 0) visits += (unsigned long long)(max(abs(b.r1 - b.r0), abs(b.c1 - b.c0)) + 1);
+    if (b.mr >= 0) marks += 1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    visits += __shfl_xor_sync(0xffffffffu, visits, o);
+    marks += __shfl_xor_sync(0xffffffffu, marks, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out3[0], visits);
+    atomicAdd(&out3[1], marks);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out3[2], (unsigned long long)total);
+}
+
 /* clearCell (map_updater.h:61-71).  v - 10.0 is evaluated in double by the reference; for every float v the
  * float subtraction rounds identically (the double difference is exact for |v| < 2^31 and rounds back to v above). */
 __device__ __forceinline__ float himm_clear(float v) {
@@ -81,60 +102,210 @@ __device__ __forceinline__ float himm_mark(float v) {
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
- * K1: tile-owner update kernel.
- *   SUB        sub-tile edge (cells) owned by one warp; smem pitch SUB+1 floats -> conflict-free along both axes
- *   WR x WC    warps per CTA tile (rows x cols) -> CTA tile = (SUB*WR) x (SUB*WC) cells
- *   LIST_CAP   beams per chunk (list of beams crossing the CTA tile, kept in sample order)
+ * K1: tile-owner update kernel.  One WARP (= one CTA of 32 threads) owns one SUB x SUB tile of one robot's grid.
+ *
+ * Cell storage in shared memory: HIMM values live in the closed set {NaN, 0, 10, ..., 180} (clearCell / markCell map
+ * the set into itself), so a staged tile holds one BYTE per cell: code = value/10 (0..18), 19 = NaN.  That is 4x less
+ * shared memory than floats => ~26 resident warps per SM instead of 10, which is what hides the dependent
+ * LDS -> op -> STS latency of the in-order walk.  Tiles are converted on load / store (float layers in HBM keep the
+ * grid_map layout).  A tile that holds any other value (foreign data uploaded by the host) is processed by the same
+ * code through a float view directly on global memory: slower, still exact.
+ *   SUB        tile edge (cells); byte pitch SUB+4 -> conflict-free walks along rows and along columns
+ *   LIST_CAP   beams per chunk (ordered list of the beams whose bounding box touches the tile)
+ * One-warp CTAs let the hardware scheduler balance the very uneven per-tile work (the tile that contains the robot
+ * sees every beam) and need no block barriers at all.
  * ------------------------------------------------------------------------------------------------------------- */
-template <int SUB, int WR, int WC, int LIST_CAP>
+template <int SUB, int LIST_CAP>
 struct HimmTileCfg {
-  static constexpr int kWarps = WR * WC;
-  static constexpr int kThreads = 32 * kWarps;
-  static constexpr int kPitch = SUB + 1;
-  static constexpr int kTileR = SUB * WR;
-  static constexpr int kTileC = SUB * WC;
-  static constexpr int kSubFloats = SUB * kPitch;
-  static constexpr size_t kSmemBytes = sizeof(float) * kSubFloats * kWarps + sizeof(uint16_t) * LIST_CAP +
-                                       sizeof(int) * (2 * kWarps);
-  static constexpr int kColWords = SUB / 32; /* 32-bit words of the per-warp column mask */
-  static_assert(SUB % 32 == 0 && SUB <= 128, "SUB must be 32, 64, 96 or 128");
+  static constexpr int kThreads = 32;
+  static constexpr int kPitch = SUB + 4; /* bytes; (SUB+4)/4 is odd for SUB = 64 -> column walks hit 32 banks */
+  static constexpr int kTileR = SUB;
+  static constexpr int kTileC = SUB;
+  static constexpr int kTileBytes = SUB * kPitch;
+  static constexpr size_t kSmemBytes = kTileBytes + sizeof(uint16_t) * LIST_CAP;
+  static_assert(SUB == 64, "tile edge is 64 (two rows per lane, 64-bit column masks)");
 };
 
-template <int SUB>
-struct ColMask {
-  uint32_t w[SUB / 32];
+#define HIMM_CODE_NAN 19
+
+/* float -> code; returns 255 for a value outside the HIMM set */
+__device__ __forceinline__ unsigned himm_encode(float v) {
+  if (v != v) return HIMM_CODE_NAN;
+  const int c = __float2int_rn(v * 0.1f);
+  /* -0.0f compares equal to 0 but has another bit pattern: keep it out of the set so it round-trips */
+  return (c >= 0 && c <= 18 && (float)(c * 10) == v && __float_as_uint(v) != 0x80000000u) ? (unsigned)c : 255u;
+}
+__device__ __forceinline__ float himm_decode(unsigned c) {
+  return c == HIMM_CODE_NAN ? __int_as_float(0x7fc00000) : (float)(int)(c * 10u);
+}
+
+/* Tile views: the walk is written once against this interface. */
+struct CodeView { /* shared memory, one byte per cell */
+  uint8_t* p;
+  __device__ __forceinline__ void clear(int off, bool mark) const {
+    int c = p[off];
+    c = (c == HIMM_CODE_NAN) ? 0 : max(c - 1, 0);             /* clearCell */
+    if (mark) c = (c <= 15) ? c + 3 : c;                       /* markCell (c is never NaN here) */
+    p[off] = (uint8_t)c;
+  }
+  __device__ __forceinline__ void mark(int off) const {
+    int c = p[off];
+    c = (c == HIMM_CODE_NAN || c == 0) ? 3 : ((c <= 15) ? c + 3 : c);
+    p[off] = (uint8_t)c;
+  }
+};
+struct FloatView { /* global memory, in place (tiles with values outside the HIMM set) */
+  volatile float* p;
+  __device__ __forceinline__ void clear(int off, bool mark) const {
+    float v = himm_clear(p[off]);
+    if (mark) v = himm_mark(v);
+    p[off] = v;
+  }
+  __device__ __forceinline__ void mark(int off) const { p[off] = himm_mark(p[off]); }
 };
 
-template <int SUB>
-__device__ __forceinline__ void colmask_add_range(ColMask<SUB>& m, int lo, int hi) {
-#pragma unroll
-  for (int k = 0; k < SUB / 32; k++) {
-    const int a = max(lo - 32 * k, 0), b = min(hi - 32 * k, 31);
-    if (a <= b) m.w[k] |= (0xffffffffu >> (31 - (b - a))) << a;
+/* Apply the listed beams, in order, to one tile through `view` (cell (r,c) of the tile lives at
+ * view[(c-C0)*pitch + (r-R0)]).  32 list entries per batch; see the schedule description below. */
+template <class View>
+__device__ __forceinline__ void himm_apply_list(const View view, const int pitch, const BeamSeg* __restrict__ segs,
+                                                const uint16_t* list, const int n_list, const int R0, const int R1,
+                                                const int C0, const int C1, const int lane) {
+  /* Lane-parallel set-up: lane L clips beam L of the batch to this tile and derives the Bresenham state at its
+   * first step inside.  Then one of two exact schedules:
+   *  (fan)     all beams of the batch start in the SAME cell (a lidar scan).  A cell at step t of such a line has
+   *            Chebyshev distance exactly t from that cell, so two beams can only share a cell at EQUAL step index.
+   *            Lane L walks its own beam, skewed so that at time tau it is at step tau - L: at any instant all lanes
+   *            are at different steps => different cells (no conflicts, no atomics), and a shared cell is reached in
+   *            lane order == sample order.  The +30 mark is applied by the same lane right after the clear of its
+   *            end cell.
+   *  (general) anything else (clipped rays, mixed origins, mark without a line): one beam at a time, the 32 lanes
+   *            striding over its cells (a Bresenham line never visits a cell twice). */
+  BeamSeg nb;
+  nb.r0 = -1;
+  nb.mr = -1;
+  if (lane < n_list) nb = segs[list[lane]];
+  for (int j0 = 0; j0 < n_list; j0 += 32) {
+    const int j = j0 + lane;
+    const BeamSeg b = nb;
+    const bool have = j < n_list;
+    /* prefetch the next batch's segments (hides the L2 latency behind this batch's walk) */
+    nb.r0 = -1;
+    nb.mr = -1;
+    if (j + 32 < n_list) nb = segs[list[j + 32]];
+    int my_len = 0, my_t0 = 0, my_off0 = 0, my_rem0 = 0, my_dm = 0, my_dn = 0, my_add = 0, my_den = 1, my_moff = -1;
+    int my_r0 = -1, my_c0 = -1;
+    bool mark_at_end = false; /* the mark cell is the last cell of my segment */
+    if (have) {
+      const bool has_mark = b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1;
+      if (has_mark) my_moff = (b.mc - C0) * pitch + (b.mr - R0);
+      if (b.r0 >= 0) {
+        const LineForm f = line_form(b);
+        int t0, t1;
+        if (clip_line_to_rect(f, R0, R1, C0, C1, t0, t1)) {
+          const unsigned den = (unsigned)max(f.den, 1);
+          const unsigned x0 = (unsigned)(f.den >> 1) + (unsigned)t0 * (unsigned)f.add;
+          const unsigned q0 = x0 / den;
+          my_rem0 = (int)(x0 - q0 * den);
+          const int mj = f.m0 + f.sm * t0, mn = f.n0 + f.sn * (int)q0;
+          const int r = f.row_major ? mj : mn, c = f.row_major ? mn : mj;
+          my_off0 = (c - C0) * pitch + (r - R0);
+          my_dm = f.row_major ? f.sm : f.sm * pitch;
+          my_dn = f.row_major ? f.sn * pitch : f.sn;
+          my_add = f.add;
+          my_den = (int)den;
+          my_len = t1 - t0 + 1;
+          my_t0 = t0;
+          my_r0 = b.r0;
+          my_c0 = b.c0;
+          mark_at_end = has_mark && t1 == f.den && b.r1 == b.mr && b.c1 == b.mc;
+        }
+      }
+    }
+    const bool has_work = my_len > 0 || my_moff >= 0;
+    unsigned active = __ballot_sync(0xffffffffu, has_work);
+    if (active == 0u) continue;
+    /* fan test: every lane with work has a segment, marks sit on segment ends, one common start cell */
+    const int lead = __ffs(active) - 1;
+    const int lr0 = __shfl_sync(0xffffffffu, my_r0, lead), lc0 = __shfl_sync(0xffffffffu, my_c0, lead);
+    const bool lane_ok = !has_work || (my_len > 0 && my_r0 == lr0 && my_c0 == lc0 && (my_moff < 0 || mark_at_end));
+    if (__all_sync(0xffffffffu, lane_ok)) {
+      /* ---- fan schedule ---- */
+      const int first = (my_len > 0) ? my_t0 + lane : 0x7fffffff;
+      const int last = (my_len > 0) ? my_t0 + my_len - 1 + lane : -0x7fffffff;
+      const int tau0 = __reduce_min_sync(0xffffffffu, first), tau1 = __reduce_max_sync(0xffffffffu, last);
+      int off = my_off0, rem = my_rem0;
+      const bool do_mark = my_moff >= 0;
+      for (int tau = tau0; tau <= tau1; tau++) {
+        if (tau >= first && tau <= last) {
+          view.clear(off, do_mark && tau == last);
+          rem += my_add;
+          off += my_dm;
+          if (rem >= my_den) {
+            rem -= my_den;
+            off += my_dn;
+          }
+        }
+        __syncwarp();
+      }
+    } else {
+      /* ---- general schedule ---- */
+      while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        const int len = __shfl_sync(0xffffffffu, my_len, src);
+        const int moff = __shfl_sync(0xffffffffu, my_moff, src);
+        if (len > 0) {
+          const int off0 = __shfl_sync(0xffffffffu, my_off0, src);
+          const int rem0 = __shfl_sync(0xffffffffu, my_rem0, src);
+          const int dm = __shfl_sync(0xffffffffu, my_dm, src);
+          const int dn = __shfl_sync(0xffffffffu, my_dn, src);
+          const int add = __shfl_sync(0xffffffffu, my_add, src);
+          const int den = __shfl_sync(0xffffffffu, my_den, src);
+          /* lane L starts at step t0+L: floor((rem0 + L*add)/den) <= 32, exact through a float reciprocal */
+          const float rcp = __frcp_rn((float)den);
+          const int x = rem0 + lane * add;
+          const int q = small_quotient(x, rcp);
+          int rem = x - q * den;
+          int off = off0 + lane * dm + q * dn;
+          const int x32 = 32 * add;
+          const int q32 = small_quotient(x32, rcp);
+          const int r32 = x32 - q32 * den;
+          const int step = 32 * dm + q32 * dn;
+          for (int k = lane; k < len; k += 32) {
+            view.clear(off, false);
+            rem += r32;
+            off += step;
+            if (rem >= den) {
+              rem -= den;
+              off += dn;
+            }
+          }
+          __syncwarp();
+        }
+        if (moff >= 0) {
+          if (lane == 0) view.mark(moff);
+          __syncwarp();
+        }
+      }
+    }
   }
 }
 
-template <int SUB, int WR, int WC, int LIST_CAP>
-__global__ void __launch_bounds__(32 * WR * WC) himm_tile_kernel(HimmArgs a) {
-  using Cfg = HimmTileCfg<SUB, WR, WC, LIST_CAP>;
+template <int SUB, int LIST_CAP>
+__global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
+  using Cfg = HimmTileCfg<SUB, LIST_CAP>;
   extern __shared__ __align__(16) unsigned char himm_smem_raw[];
-  float* tiles = reinterpret_cast<float*>(himm_smem_raw);
-  uint16_t* list = reinterpret_cast<uint16_t*>(tiles + Cfg::kSubFloats * Cfg::kWarps);
-  int* warp_cnt = reinterpret_cast<int*>(list + LIST_CAP);
+  uint8_t* tile = himm_smem_raw;
+  uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + Cfg::kTileBytes);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x;
   const int robot = a.robot0 + blockIdx.y;
   const int tile_r = blockIdx.x % a.tiles_r, tile_c = blockIdx.x / a.tiles_r;
   const int rows = a.dims.rows, cols = a.dims.cols;
 
-  /* CTA tile rectangle (inclusive, clipped to the grid). */
-  const int TR0 = tile_r * Cfg::kTileR, TC0 = tile_c * Cfg::kTileC;
-  const int TR1 = min(TR0 + Cfg::kTileR, rows) - 1, TC1 = min(TC0 + Cfg::kTileC, cols) - 1;
-  /* This warp's sub-tile rectangle. */
-  const int wr = warp % WR, wc = warp / WR;
-  const int R0 = TR0 + wr * SUB, C0 = TC0 + wc * SUB;
+  /* tile rectangle (inclusive, clipped to the grid) */
+  const int R0 = tile_r * SUB, C0 = tile_c * SUB;
   const int R1 = min(R0 + SUB, rows) - 1, C1 = min(C0 + SUB, cols) - 1;
-  const bool warp_has_cells = (R0 <= R1) && (C0 <= C1);
 
   int beg, end;
   if (a.single_n >= 0) {
@@ -146,178 +317,132 @@ __global__ void __launch_bounds__(32 * WR * WC) himm_tile_kernel(HimmArgs a) {
   }
   if (beg >= end) return;
 
-  float* tile = tiles + warp * Cfg::kSubFloats;
   float* gbase = a.layer + (size_t)robot * rows * cols;
-  ColMask<SUB> loaded;
-#pragma unroll
-  for (int k = 0; k < SUB / 32; k++) loaded.w[k] = 0u;
+  float* gtile = gbase + (size_t)C0 * rows + R0;
+  unsigned long long loaded = 0ull; /* columns staged in shared memory (bit c = column C0+c) */
+  bool foreign = false;             /* tile holds values outside the HIMM set -> float view on global memory */
+  const bool row_lo_ok = R0 + lane <= R1, row_hi_ok = R0 + lane + 32 <= R1;
 
   for (int base = beg; base < end; base += LIST_CAP) {
     const int chunk_end = min(base + LIST_CAP, end);
+    const BeamSeg* segs = a.segs + base;
+    const int n_chunk = chunk_end - base;
 
-    /* ---- CTA filter: ordered list of the beams whose bounding box (or mark cell) touches the CTA tile ---- */
-    int n_list = 0; /* uniform across the CTA */
-    for (int i0 = base, it = 0; i0 < chunk_end; i0 += Cfg::kThreads, it++) {
-      const int i = i0 + tid;
-      bool hit = false;
-      if (i < chunk_end) {
-        const BeamSeg b = a.segs[i];
-        if (b.r0 >= 0) {
-          hit = max(b.r0, b.r1) >= TR0 && min(b.r0, b.r1) <= TR1 && max(b.c0, b.c1) >= TC0 && min(b.c0, b.c1) <= TC1;
-        }
-        if (b.mr >= 0) hit = hit || (b.mr >= TR0 && b.mr <= TR1 && b.mc >= TC0 && b.mc <= TC1);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      int* cnt = warp_cnt + (it & 1) * Cfg::kWarps; /* double-buffered: one barrier per step */
-      if (lane == 0) cnt[warp] = __popc(bal);
-      __syncthreads();
-      int off = n_list, tot = 0;
+    /* ---- filter: ordered list of the beams whose bounding box (or mark cell) touches the tile.  4 independent
+     * 24-byte loads per lane are in flight per round. ---- */
+    int n_list = 0; /* warp-uniform */
+    unsigned long long need = 0ull;
+    for (int i0 = 0; i0 < n_chunk; i0 += 128) {
+      BeamSeg b4[4];
 #pragma unroll
-      for (int w = 0; w < Cfg::kWarps; w++) {
-        const int cw = cnt[w];
-        if (w < warp) off += cw;
-        tot += cw;
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + 32 * u + lane;
+        b4[u].r0 = -1;
+        b4[u].mr = -1;
+        if (i < n_chunk) b4[u] = segs[i];
       }
-      if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(i - base);
-      n_list += tot;
-    }
-    __syncthreads();
-
-    if (warp_has_cells && n_list > 0) {
-      /* ---- pass A: which columns of this warp's sub-tile will be touched? ---- */
-      ColMask<SUB> need;
 #pragma unroll
-      for (int k = 0; k < SUB / 32; k++) need.w[k] = 0u;
-      for (int j0 = 0; j0 < n_list; j0 += 32) {
-        const int j = j0 + lane;
-        if (j < n_list) {
-          const BeamSeg b = a.segs[base + list[j]];
-          if (b.r0 >= 0) {
-            const LineForm f = line_form(b);
-            int t0, t1;
-            if (clip_line_to_rect(f, R0, R1, C0, C1, t0, t1)) {
-              /* columns at t0 and t1 (monotone in between) */
-              int ca, cb;
-              if (f.row_major) {
-                const int den = max(f.den, 1);
-                ca = f.n0 + f.sn * (int)(((unsigned)(f.den >> 1) + (unsigned)t0 * (unsigned)f.add) / (unsigned)den);
-                cb = f.n0 + f.sn * (int)(((unsigned)(f.den >> 1) + (unsigned)t1 * (unsigned)f.add) / (unsigned)den);
-              } else {
-                ca = f.m0 + f.sm * t0;
-                cb = f.m0 + f.sm * t1;
-              }
-              colmask_add_range<SUB>(need, min(ca, cb) - C0, max(ca, cb) - C0);
-            }
+      for (int u = 0; u < 4; u++) {
+        const BeamSeg b = b4[u];
+        bool hit = false;
+        if (b.r0 >= 0 && max(b.r0, b.r1) >= R0 && min(b.r0, b.r1) <= R1) {
+          /* columns the beam may touch inside this tile (bounding box: conservative) */
+          const int ca = max(min(b.c0, b.c1), C0), cb = min(max(b.c0, b.c1), C1);
+          if (ca <= cb) {
+            hit = true;
+            need |= (~0ull >> (63 - (cb - ca))) << (ca - C0);
           }
-          if (b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1) colmask_add_range<SUB>(need, b.mc - C0, b.mc - C0);
         }
+        if (b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1) {
+          hit = true;
+          need |= 1ull << (b.mc - C0);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(i0 + 32 * u + lane);
+        n_list += __popc(bal);
       }
+    }
+    __syncwarp();
+    if (n_list == 0) continue;
+
+    if (!foreign) {
+      /* ---- stage the newly needed columns: float -> code, 8 columns (16 loads per lane) in flight per round ---- */
+      unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)need), hi = __reduce_or_sync(0xffffffffu, (unsigned)(need >> 32));
+      unsigned long long m = (((unsigned long long)hi << 32) | lo) & ~loaded;
+      loaded |= m;
+      unsigned bad = 0;
+      while (m) {
+        int cidx[8];
+        float v0[8], v1[8];
 #pragma unroll
-      for (int k = 0; k < SUB / 32; k++) {
-        need.w[k] = __reduce_or_sync(0xffffffffu, need.w[k]) & ~loaded.w[k];
-      }
-      /* ---- stage the newly needed columns (coalesced: one column = SUB consecutive floats) ---- */
+        for (int u = 0; u < 8; u++) {
+          cidx[u] = m ? __ffsll((long long)m) - 1 : -1;
+          if (m) m &= m - 1;
+        }
 #pragma unroll
-      for (int k = 0; k < SUB / 32; k++) {
-        unsigned m = need.w[k];
-        loaded.w[k] |= m;
-        while (m) {
-          const int c = 32 * k + __ffs(m) - 1;
-          m &= m - 1;
-          const float* src = gbase + (size_t)(C0 + c) * rows + R0;
+        for (int u = 0; u < 8; u++) {
+          v0[u] = v1[u] = 0.f;
+          if (cidx[u] >= 0) {
+            const float* src = gtile + (size_t)cidx[u] * rows + lane;
+            if (row_lo_ok) v0[u] = src[0];
+            if (row_hi_ok) v1[u] = src[32];
+          }
+        }
 #pragma unroll
-          for (int r = lane; r < SUB; r += 32)
-            if (R0 + r <= R1) tile[c * Cfg::kPitch + r] = __ldg(src + r);
+        for (int u = 0; u < 8; u++) {
+          if (cidx[u] >= 0) {
+            const unsigned c0 = himm_encode(v0[u]), c1 = himm_encode(v1[u]);
+            bad |= (row_lo_ok && c0 == 255u) || (row_hi_ok && c1 == 255u);
+            tile[cidx[u] * Cfg::kPitch + lane] = (uint8_t)c0;
+            tile[cidx[u] * Cfg::kPitch + lane + 32] = (uint8_t)c1;
+          }
         }
       }
       __syncwarp();
-
-      /* ---- pass B: apply the beams in sample order ---- */
-      for (int j0 = 0; j0 < n_list; j0 += 32) {
-        const int j = j0 + lane;
-        /* lane-parallel set-up of up to 32 segments */
-        int my_len = 0, my_off0 = 0, my_rem0 = 0, my_dm = 0, my_dn = 0, my_add = 0, my_den = 1, my_moff = -1;
-        if (j < n_list) {
-          const BeamSeg b = a.segs[base + list[j]];
-          if (b.r0 >= 0) {
-            const LineForm f = line_form(b);
-            int t0, t1;
-            if (clip_line_to_rect(f, R0, R1, C0, C1, t0, t1)) {
-              const unsigned den = (unsigned)max(f.den, 1);
-              const unsigned x0 = (unsigned)(f.den >> 1) + (unsigned)t0 * (unsigned)f.add;
-              const unsigned q0 = x0 / den;
-              my_rem0 = (int)(x0 - q0 * den);
-              const int mj = f.m0 + f.sm * t0, mn = f.n0 + f.sn * (int)q0;
-              const int r = f.row_major ? mj : mn, c = f.row_major ? mn : mj;
-              my_off0 = (c - C0) * Cfg::kPitch + (r - R0);
-              my_dm = f.row_major ? f.sm : f.sm * Cfg::kPitch;
-              my_dn = f.row_major ? f.sn * Cfg::kPitch : f.sn;
-              my_add = f.add;
-              my_den = (int)den;
-              my_len = t1 - t0 + 1;
-            }
-          }
-          if (b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1)
-            my_moff = (b.mc - C0) * Cfg::kPitch + (b.mr - R0);
-        }
-        unsigned active = __ballot_sync(0xffffffffu, my_len > 0 || my_moff >= 0);
-        while (active) {
-          const int src = __ffs(active) - 1;
-          active &= active - 1;
-          const int len = __shfl_sync(0xffffffffu, my_len, src);
-          const int moff = __shfl_sync(0xffffffffu, my_moff, src);
-          if (len > 0) {
-            const int off0 = __shfl_sync(0xffffffffu, my_off0, src);
-            const int rem0 = __shfl_sync(0xffffffffu, my_rem0, src);
-            const int dm = __shfl_sync(0xffffffffu, my_dm, src);
-            const int dn = __shfl_sync(0xffffffffu, my_dn, src);
-            const int add = __shfl_sync(0xffffffffu, my_add, src);
-            const int den = __shfl_sync(0xffffffffu, my_den, src);
-            /* lane L starts at step t0+L: floor((rem0 + L*add)/den) <= 32, exact through a float reciprocal
-             * (x + 0.5 keeps the quotient >= 0.5/den away from an integer; float error here < 5e-6). */
-            const float rcp = __frcp_rn((float)den);
-            const int x = rem0 + lane * add;
-            const int q = small_quotient(x, rcp);
-            int rem = x - q * den;
-            int off = off0 + lane * dm + q * dn;
-            const int x32 = 32 * add;
-            const int q32 = small_quotient(x32, rcp);
-            const int r32 = x32 - q32 * den;
-            const int step = 32 * dm + q32 * dn;
-            for (int k = lane; k < len; k += 32) {
-              tile[off] = himm_clear(tile[off]);
-              rem += r32;
-              off += step;
-              if (rem >= den) {
-                rem -= den;
-                off += dn;
-              }
-            }
-            __syncwarp();
-          }
-          if (moff >= 0) {
-            if (lane == 0) tile[moff] = himm_mark(tile[moff]);
-            __syncwarp();
-          }
-        }
+      if (__any_sync(0xffffffffu, bad)) {
+        /* Foreign values: nothing has been modified yet in this chunk; columns staged by EARLIER chunks hold
+         * HIMM-set values only and are flushed first, then everything continues in place on global memory. */
+        foreign = true;
       }
     }
-    __syncthreads(); /* the list is rewritten by the next chunk */
+    if (foreign && loaded) {
+      unsigned long long m = loaded;
+      loaded = 0ull;
+      /* columns that failed to encode were staged in this very chunk and are unmodified: skip the flush for any
+       * column containing a 255 code (its global data is still the truth). */
+      while (m) {
+        const int c = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const unsigned c0 = tile[c * Cfg::kPitch + lane], c1 = tile[c * Cfg::kPitch + lane + 32];
+        const bool col_bad = __any_sync(0xffffffffu, (row_lo_ok && c0 == 255u) || (row_hi_ok && c1 == 255u));
+        if (!col_bad) {
+          float* dst = gtile + (size_t)c * rows + lane;
+          if (row_lo_ok) dst[0] = himm_decode(c0);
+          if (row_hi_ok) dst[32] = himm_decode(c1);
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+    }
+
+    /* ---- apply the beams in sample order ---- */
+    if (!foreign)
+      himm_apply_list(CodeView{tile}, Cfg::kPitch, segs, list, n_list, R0, R1, C0, C1, lane);
+    else
+      himm_apply_list(FloatView{gtile}, rows, segs, list, n_list, R0, R1, C0, C1, lane);
+    __syncwarp(); /* the list is rewritten by the next chunk */
   }
 
-  /* ---- write back the staged (== touched) columns ---- */
-  if (warp_has_cells) {
-#pragma unroll
-    for (int k = 0; k < SUB / 32; k++) {
-      unsigned m = loaded.w[k];
-      while (m) {
-        const int c = 32 * k + __ffs(m) - 1;
-        m &= m - 1;
-        float* dst = gbase + (size_t)(C0 + c) * rows + R0;
-#pragma unroll
-        for (int r = lane; r < SUB; r += 32)
-          if (R0 + r <= R1) dst[r] = tile[c * Cfg::kPitch + r];
-      }
+  /* ---- write back the staged (== possibly touched) columns: code -> float, coalesced 256-byte segments ---- */
+  {
+    unsigned long long m = loaded;
+    while (m) {
+      const int c = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      float* dst = gtile + (size_t)c * rows + lane;
+      const unsigned c0 = tile[c * Cfg::kPitch + lane], c1 = tile[c * Cfg::kPitch + lane + 32];
+      if (row_lo_ok) dst[0] = himm_decode(c0);
+      if (row_hi_ok) dst[32] = himm_decode(c1);
     }
   }
 }

@@ -95,6 +95,12 @@ class DeviceGridMap:
         check(lib().b200nav_himm_update_batched_dev(self.h, layer.encode(), ptr(dev_samples), ptr(dev_offsets),
                                                     int(total)), self.ctx.h)
 
+    def himm_last_stats(self):
+        """(cell visits, marks, beams) of the last update (roofline accounting)."""
+        out = np.zeros(3, np.int64)
+        check(lib().b200nav_himm_last_stats(self.h, out.ctypes.data), self.ctx.h)
+        return int(out[0]), int(out[1]), int(out[2])
+
     def close(self):
         if self.h:
             lib().b200nav_grid_destroy(self.h)
