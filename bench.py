@@ -264,7 +264,7 @@ class GpuArm:
 
     def step_dev(self, i):
         c = i % N_CYCLES
-        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c])
+        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c], self.cfg["beams"])
         self.vfh.update_batched_dev(self.grid, "master", self.cyc.inputs[c], self.cmd)
         self.all_gather()
 
@@ -287,7 +287,7 @@ class GpuArm:
 
     def algorithmic_bytes(self, c):
         """8 B per cell visit + 8 B per mark + 36 B per beam, for cycle c (this rank)."""
-        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c])
+        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c], self.cfg["beams"])
         visits, marks, beams = self.grid.himm_last_stats()
         return 8 * visits + 8 * marks + 36 * beams, visits, marks, beams
 

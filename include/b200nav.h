@@ -126,9 +126,11 @@ int b200nav_himm_update(b200nav_grid* grid, int robot, const char* layer, const 
  * each robot's samples applied in order to its own map.  bbox: n_robots*4 doubles in/out, or NULL. */
 int b200nav_himm_update_batched(b200nav_grid* grid, const char* layer, const b200nav_sample* host_samples,
                                 const int32_t* host_offsets, double* bbox);
-/* Same with samples/offsets already in device memory; asynchronous (no stream sync).  total = offsets[n_robots]. */
+/* Same with samples/offsets already in device memory; asynchronous (no stream sync).  total = offsets[n_robots];
+ * max_samples_per_robot = an upper bound of offsets[r+1]-offsets[r] (sizes the binning scratch; a robot exceeding
+ * it is reported as B200NAV_ERANGE by the next b200nav_himm_last_stats call). */
 int b200nav_himm_update_batched_dev(b200nav_grid* grid, const char* layer, const b200nav_sample* dev_samples,
-                                    const int32_t* dev_offsets, int total);
+                                    const int32_t* dev_offsets, int total, int max_samples_per_robot);
 
 /* Work statistics of the LAST himm update of this grid (all robots of that call): out[0] = cell visits
  * (sum over beams of the Bresenham cell count), out[1] = marks, out[2] = beams.  Used for the algorithmic-byte

@@ -66,7 +66,7 @@ _SIGNATURES = {
     "b200nav_grid_layer_devptr": (C.c_void_p, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_update": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200nav_himm_update_batched": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "b200nav_himm_update_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "b200nav_himm_update_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "b200nav_vfh_default_params": (None, [C.POINTER(VfhParamsC)]),
     "b200nav_vfh_create": (C.c_int, [C.c_void_p, C.POINTER(VfhParamsC), C.c_int, C.POINTER(C.c_void_p)]),
     "b200nav_vfh_destroy": (C.c_int, [C.c_void_p]),

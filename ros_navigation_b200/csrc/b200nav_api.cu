@@ -109,7 +109,8 @@ struct b200nav_grid {
   std::vector<RobotGeom> geom_host;
   RobotGeom* geom_dev = nullptr;
   std::map<std::string, Layer> layers;
-  DevBuf samples, segs, offsets, occ, stats;
+  DevBuf samples, segs, offsets, occ, stats, beam_masks, col_masks, errflag;
+  size_t masks_zeroed_bytes = 0, colmasks_zeroed_bytes = 0;
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
 };
@@ -211,11 +212,32 @@ int upload_geom(b200nav_grid* g) {
 constexpr int kVfhMaxSmem = 200 * 1024;
 
 /* ---- HIMM launch ------------------------------------------------------------------------------------------- */
-constexpr int kSub = 64, kListCap = 2048;
+constexpr int kSub = HIMM_TILE, kListCap = HIMM_CHUNK;
 using TileCfg = HimmTileCfg<kSub, kListCap>;
 
+/* Binning scratch: grow-only, kept all-zero between updates (the tile kernel clears what it consumes). */
+int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total) {
+  b200nav_ctx* ctx = g->ctx;
+  const size_t mb = n_tiles_total * HIMM_MASK_WORDS * sizeof(uint32_t), cb = n_tiles_total * sizeof(unsigned long long);
+  if (mb > g->beam_masks.cap) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, g->beam_masks.reserve(mb));
+    CUDA_TRY(ctx, cudaMemsetAsync(g->beam_masks.p, 0, g->beam_masks.cap, ctx->stream));
+  }
+  if (cb > g->col_masks.cap) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, g->col_masks.reserve(cb));
+    CUDA_TRY(ctx, cudaMemsetAsync(g->col_masks.p, 0, g->col_masks.cap, ctx->stream));
+  }
+  if (!g->errflag.p) {
+    CUDA_TRY(ctx, g->errflag.reserve(sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(g->errflag.p, 0, sizeof(int), ctx->stream));
+  }
+  return B200NAV_OK;
+}
+
 int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
-                int robot0, int n_active, int single_n, int total) {
+                int robot0, int n_active, int single_n, int total, int max_per_robot) {
   b200nav_ctx* ctx = g->ctx;
   if (total <= 0) return B200NAV_OK;
   CUDA_TRY(ctx, g->segs.reserve(sizeof(BeamSeg) * (size_t)total));
@@ -232,12 +254,19 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   a.total = total;
   a.tiles_r = (g->dims.rows + TileCfg::kTileR - 1) / TileCfg::kTileR;
   a.tiles_c = (g->dims.cols + TileCfg::kTileC - 1) / TileCfg::kTileC;
+  a.n_chunks = std::max(1, (max_per_robot + HIMM_CHUNK - 1) / HIMM_CHUNK);
+  const size_t n_tiles_total = (size_t)n_active * a.n_chunks * a.tiles_r * a.tiles_c;
+  int rc = himm_reserve_masks(g, n_tiles_total);
+  if (rc) return rc;
+  a.beam_masks = static_cast<uint32_t*>(g->beam_masks.p);
+  a.col_masks = static_cast<unsigned long long*>(g->col_masks.p);
+  a.error_flag = static_cast<int*>(g->errflag.p);
   g->last_total = total;
   {
     ProfScope ps(ctx, PROF_HIMM_PREP);
     himm_prep_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(a);
   }
-  int rc = check_launch(ctx, "himm_prep_kernel");
+  rc = check_launch(ctx, "himm_prep_kernel");
   if (rc) return rc;
   auto kern = himm_tile_kernel<kSub, kListCap>;
   dim3 grid((unsigned)(a.tiles_r * a.tiles_c), (unsigned)n_active);
@@ -246,6 +275,20 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
     kern<<<grid, TileCfg::kThreads, TileCfg::kSmemBytes, ctx->stream>>>(a);
   }
   return check_launch(ctx, "himm_tile_kernel");
+}
+
+/* Reports (and clears) the device-side "more samples than declared" flag; call after a stream sync. */
+int himm_check_error_flag(b200nav_grid* g) {
+  if (!g->errflag.p) return B200NAV_OK;
+  int flag = 0;
+  CUDA_TRY(g->ctx, cudaMemcpy(&flag, g->errflag.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(g->errflag.p, 0, sizeof(int));
+    return set_err(g->ctx, B200NAV_ERANGE,
+                   "a robot had more samples than max_samples_per_robot: its excess samples were ignored and the "
+                   "binning scratch may hold stale bits (destroy the grid)");
+  }
+  return B200NAV_OK;
 }
 
 void host_touch(const b200nav_sample* s, int n, double* bbox) {
@@ -517,6 +560,9 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   g->offsets.release();
   g->occ.release();
   g->stats.release();
+  g->beam_masks.release();
+  g->col_masks.release();
+  g->errflag.release();
   delete g;
   return B200NAV_OK;
 }
@@ -732,7 +778,7 @@ int b200nav_himm_update(b200nav_grid* g, int robot, const char* layer, const b20
   CUDA_TRY(ctx, g->samples.reserve(sizeof(b200nav_sample) * (size_t)n));
   CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_samples, sizeof(b200nav_sample) * (size_t)n,
                                 cudaMemcpyHostToDevice, ctx->stream));
-  int rc = himm_launch(g, l->dev, static_cast<const b200nav_sample*>(g->samples.p), nullptr, robot, 1, n, n);
+  int rc = himm_launch(g, l->dev, static_cast<const b200nav_sample*>(g->samples.p), nullptr, robot, 1, n, n, n);
   if (rc) return rc;
   if (bbox) host_touch(host_samples, n, bbox); /* overlaps the kernels */
   return sync_stream(ctx);
@@ -758,8 +804,10 @@ int b200nav_himm_update_batched(b200nav_grid* g, const char* layer, const b200na
                                 cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(g->offsets.p, host_offsets, sizeof(int32_t) * (size_t)(nr + 1),
                                 cudaMemcpyHostToDevice, ctx->stream));
+  int max_per = 0;
+  for (int r = 0; r < nr; r++) max_per = std::max(max_per, host_offsets[r + 1] - host_offsets[r]);
   int rc = himm_launch(g, l->dev, static_cast<const b200nav_sample*>(g->samples.p),
-                       static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total);
+                       static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per);
   if (rc) return rc;
   if (bbox)
     for (int r = 0; r < nr; r++)
@@ -768,12 +816,13 @@ int b200nav_himm_update_batched(b200nav_grid* g, const char* layer, const b200na
 }
 
 int b200nav_himm_update_batched_dev(b200nav_grid* g, const char* layer, const b200nav_sample* dev_samples,
-                                    const int32_t* dev_offsets, int total) {
-  if (!g || !dev_offsets || total < 0 || (total > 0 && !dev_samples)) return B200NAV_EINVAL;
+                                    const int32_t* dev_offsets, int total, int max_samples_per_robot) {
+  if (!g || !dev_offsets || total < 0 || (total > 0 && !dev_samples) || max_samples_per_robot < 0)
+    return B200NAV_EINVAL;
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
-  return himm_launch(g, l->dev, dev_samples, dev_offsets, 0, g->n_robots, -1, total);
+  return himm_launch(g, l->dev, dev_samples, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot);
 }
 
 int b200nav_himm_last_stats(b200nav_grid* g, int64_t* out3) {
@@ -789,7 +838,9 @@ int b200nav_himm_last_stats(b200nav_grid* g, int64_t* out3) {
   int rc = check_launch(ctx, "himm_stats_kernel");
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(out3, g->stats.p, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  return sync_stream(ctx);
+  rc = sync_stream(ctx);
+  if (rc) return rc;
+  return himm_check_error_flag(g);
 }
 
 /* ================================================================================================================

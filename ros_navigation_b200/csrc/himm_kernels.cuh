@@ -29,6 +29,10 @@
 
 namespace b200nav {
 
+#define HIMM_TILE 64        /* tile edge in cells (one warp owns one tile)                                  */
+#define HIMM_CHUNK 2048     /* beams per chunk: one tile's beam set is a 2048-bit mask (64 words)           */
+#define HIMM_MASK_WORDS (HIMM_CHUNK / 32)
+
 struct HimmArgs {
   GridDims dims;
   const RobotGeom* geom;          /* [n_robots]                                   */
@@ -36,22 +40,40 @@ struct HimmArgs {
   const b200nav_sample* samples;  /* device                                       */
   const int32_t* offsets;         /* device [n_robots+1], or NULL in single mode  */
   BeamSeg* segs;                  /* device scratch [total]                       */
+  /* binning scratch, all-zero between updates (the tile kernel clears what it consumes):
+   *   beam_masks[robot][chunk][tile][HIMM_MASK_WORDS]  bit b = beam (chunk*HIMM_CHUNK + b) of the robot touches tile
+   *   col_masks [robot][chunk][tile]                    64-bit: columns of the tile that may be touched         */
+  uint32_t* beam_masks;
+  unsigned long long* col_masks;
+  int* error_flag;                /* set when a robot has more samples than n_chunks * HIMM_CHUNK              */
   int robot0;                     /* first robot handled by blockIdx.y == 0       */
   int n_active;                   /* robots handled by this launch                */
   int single_n;                   /* >= 0: single-robot mode, samples [0, n)      */
   int total;                      /* total samples                                */
-  int tiles_r, tiles_c;           /* CTA tiles per grid                           */
+  int tiles_r, tiles_c;           /* tiles per grid                               */
+  int n_chunks;                   /* chunks per robot                             */
 };
 
+__device__ __forceinline__ void himm_bin_tile(const HimmArgs& a, size_t rc_base, int tr, int tc, int word, uint32_t bit,
+                                              int col_lo, int col_hi) {
+  const size_t t = rc_base + (size_t)(tc * a.tiles_r + tr);
+  atomicOr(&a.beam_masks[t * HIMM_MASK_WORDS + word], bit);
+  const int c0 = max(col_lo - tc * HIMM_TILE, 0), c1 = min(col_hi - tc * HIMM_TILE, HIMM_TILE - 1);
+  if (c0 <= c1) atomicOr(&a.col_masks[t], (~0ull >> (63 - (c1 - c0))) << c0);
+}
+
 /* ---------------------------------------------------------------------------------------------------------------
- * K0: RangeSample -> BeamSeg
+ * K0: RangeSample -> BeamSeg, and binning: every tile the Bresenham line (or the mark) touches gets the beam's bit
+ * in its 2048-bit beam mask.  Bits are set with RED.OR; reading a mask in ascending bit order later yields the
+ * tile's beams in sample order without any sort.
  * ------------------------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total) return;
-  int robot;
+  int rel, beg;
   if (a.single_n >= 0) {
-    robot = a.robot0;
+    rel = 0;
+    beg = 0;
   } else {
     /* last r with offsets[r] <= i */
     int lo = 0, hi = a.n_active;
@@ -60,11 +82,51 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
       if (__ldg(&a.offsets[mid]) <= i) lo = mid;
       else hi = mid;
     }
-    robot = a.robot0 + lo;
+    rel = lo;
+    beg = __ldg(&a.offsets[lo]);
   }
-  const RobotGeom g = a.geom[robot];
+  const RobotGeom g = a.geom[a.robot0 + rel];
   const b200nav_sample s = a.samples[i];
-  a.segs[i] = make_beam(a.dims, g, s.sx, s.sy, s.ex, s.ey, s.clear_end);
+  const BeamSeg b = make_beam(a.dims, g, s.sx, s.sy, s.ex, s.ey, s.clear_end);
+  a.segs[i] = b;
+
+  const int k = i - beg; /* index of the beam within its robot */
+  const int chunk = k / HIMM_CHUNK;
+  if (chunk >= a.n_chunks) {
+    *a.error_flag = 1;
+    return;
+  }
+  const int word = (k % HIMM_CHUNK) >> 5;
+  const uint32_t bit = 1u << (k & 31);
+  const size_t rc_base = ((size_t)rel * a.n_chunks + chunk) * (size_t)(a.tiles_r * a.tiles_c);
+
+  if (b.mr >= 0) himm_bin_tile(a, rc_base, b.mr / HIMM_TILE, b.mc / HIMM_TILE, word, bit, b.mc, b.mc);
+  if (b.r0 < 0) return;
+  const LineForm f = line_form(b);
+  const unsigned den = (unsigned)max(f.den, 1);
+  const unsigned num0 = (unsigned)(f.den >> 1);
+  /* bands of HIMM_TILE along the driving axis */
+  const int m_end = f.m0 + f.sm * f.den;
+  const int band0 = f.m0 / HIMM_TILE, band1 = m_end / HIMM_TILE;
+  for (int band = band0;; band += f.sm) {
+    const int mlo = band * HIMM_TILE, mhi = mlo + HIMM_TILE - 1;
+    int ta = (f.sm > 0) ? (mlo - f.m0) : (f.m0 - mhi);
+    int tb = (f.sm > 0) ? (mhi - f.m0) : (f.m0 - mlo);
+    ta = max(ta, 0);
+    tb = min(tb, f.den);
+    const int qa = (int)((num0 + (unsigned)ta * (unsigned)f.add) / den);
+    const int qb = (int)((num0 + (unsigned)tb * (unsigned)f.add) / den);
+    const int na = f.n0 + f.sn * qa, nb = f.n0 + f.sn * qb; /* minor coordinate at both ends (monotone between) */
+    const int nlo = min(na, nb), nhi = max(na, nb);
+    const int ma = f.m0 + f.sm * ta, mb = f.m0 + f.sm * tb;
+    for (int nt = nlo / HIMM_TILE; nt <= nhi / HIMM_TILE; nt++) {
+      if (f.row_major) /* rows drive: tile (band, nt); columns = minor range inside the band */
+        himm_bin_tile(a, rc_base, band, nt, word, bit, nlo, nhi);
+      else /* columns drive: tile (nt, band); columns = the band's driving range (superset for this tile) */
+        himm_bin_tile(a, rc_base, nt, band, word, bit, min(ma, mb), max(ma, mb));
+    }
+    if (band == band1) break;
+  }
 }
 
 /* Work statistics over the BeamSegs of one update: cell visits, marks, beams (block reduce + 3 atomics per CTA). */
@@ -126,32 +188,33 @@ struct HimmTileCfg {
   static_assert(SUB == 64, "tile edge is 64 (two rows per lane, 64-bit column masks)");
 };
 
-#define HIMM_CODE_NAN 19
+/* Codes: 0 = NaN (unknown), k = value/10 + 1 for value in {0,10,...,180} (1..19).  With this numbering
+ *   clearCell(c) = max(c - 1, 1)                              (NaN -> 0; 0 stays 0)
+ *   markCell(c)  = c <= 1 ? 4 : (c <= 16 ? c + 3 : c)         (NaN or 0 -> 30; <= 150 -> +30) */
+#define HIMM_CODE_NAN 0
 
 /* float -> code; returns 255 for a value outside the HIMM set */
 __device__ __forceinline__ unsigned himm_encode(float v) {
   if (v != v) return HIMM_CODE_NAN;
   const int c = __float2int_rn(v * 0.1f);
   /* -0.0f compares equal to 0 but has another bit pattern: keep it out of the set so it round-trips */
-  return (c >= 0 && c <= 18 && (float)(c * 10) == v && __float_as_uint(v) != 0x80000000u) ? (unsigned)c : 255u;
+  return (c >= 0 && c <= 18 && (float)(c * 10) == v && __float_as_uint(v) != 0x80000000u) ? (unsigned)(c + 1) : 255u;
 }
 __device__ __forceinline__ float himm_decode(unsigned c) {
-  return c == HIMM_CODE_NAN ? __int_as_float(0x7fc00000) : (float)(int)(c * 10u);
+  return c == HIMM_CODE_NAN ? __int_as_float(0x7fc00000) : (float)(int)(c * 10u - 10u);
 }
 
 /* Tile views: the walk is written once against this interface. */
 struct CodeView { /* shared memory, one byte per cell */
   uint8_t* p;
   __device__ __forceinline__ void clear(int off, bool mark) const {
-    int c = p[off];
-    c = (c == HIMM_CODE_NAN) ? 0 : max(c - 1, 0);             /* clearCell */
-    if (mark) c = (c <= 15) ? c + 3 : c;                       /* markCell (c is never NaN here) */
+    int c = max((int)p[off] - 1, 1);                 /* clearCell */
+    if (mark) c = (c <= 16) ? c + 3 : c;             /* markCell (c >= 1 here) */
     p[off] = (uint8_t)c;
   }
   __device__ __forceinline__ void mark(int off) const {
-    int c = p[off];
-    c = (c == HIMM_CODE_NAN || c == 0) ? 3 : ((c <= 15) ? c + 3 : c);
-    p[off] = (uint8_t)c;
+    const int c = p[off];
+    p[off] = (uint8_t)((c <= 1) ? 4 : ((c <= 16) ? c + 3 : c));
   }
 };
 struct FloatView { /* global memory, in place (tiles with values outside the HIMM set) */
@@ -229,15 +292,18 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
     const int lr0 = __shfl_sync(0xffffffffu, my_r0, lead), lc0 = __shfl_sync(0xffffffffu, my_c0, lead);
     const bool lane_ok = !has_work || (my_len > 0 && my_r0 == lr0 && my_c0 == lc0 && (my_moff < 0 || mark_at_end));
     if (__all_sync(0xffffffffu, lane_ok)) {
-      /* ---- fan schedule ---- */
+      /* ---- fan schedule (skewed): lane L is at step tau - L at time tau ---- */
       const int first = (my_len > 0) ? my_t0 + lane : 0x7fffffff;
       const int last = (my_len > 0) ? my_t0 + my_len - 1 + lane : -0x7fffffff;
       const int tau0 = __reduce_min_sync(0xffffffffu, first), tau1 = __reduce_max_sync(0xffffffffu, last);
       int off = my_off0, rem = my_rem0;
-      const bool do_mark = my_moff >= 0;
-      for (int tau = tau0; tau <= tau1; tau++) {
-        if (tau >= first && tau <= last) {
-          view.clear(off, do_mark && tau == last);
+      const unsigned span = (my_len > 0) ? (unsigned)(my_len - 1) : 0u;
+      const int mark_k = (my_moff >= 0) ? (int)span : -1; /* iteration (relative to `first`) that also marks */
+      int k = tau0 - first;                               /* my step relative to my first; negative = not yet */
+      if (my_len <= 0) k = -0x40000000;
+      for (int tau = tau0; tau <= tau1; tau++, k++) {
+        if ((unsigned)k <= span) {
+          view.clear(off, k == mark_k);
           rem += my_add;
           off += my_dm;
           if (rem >= my_den) {
@@ -294,6 +360,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
 template <int SUB, int LIST_CAP>
 __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   using Cfg = HimmTileCfg<SUB, LIST_CAP>;
+  static_assert(SUB == HIMM_TILE && LIST_CAP == HIMM_CHUNK, "tile / chunk constants");
   extern __shared__ __align__(16) unsigned char himm_smem_raw[];
   uint8_t* tile = himm_smem_raw;
   uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + Cfg::kTileBytes);
@@ -307,15 +374,9 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   const int R0 = tile_r * SUB, C0 = tile_c * SUB;
   const int R1 = min(R0 + SUB, rows) - 1, C1 = min(C0 + SUB, cols) - 1;
 
-  int beg, end;
-  if (a.single_n >= 0) {
-    beg = 0;
-    end = a.single_n;
-  } else {
-    beg = __ldg(&a.offsets[blockIdx.y]);
-    end = __ldg(&a.offsets[blockIdx.y + 1]);
-  }
-  if (beg >= end) return;
+  int beg;
+  if (a.single_n >= 0) beg = 0;
+  else beg = __ldg(&a.offsets[blockIdx.y]);
 
   float* gbase = a.layer + (size_t)robot * rows * cols;
   float* gtile = gbase + (size_t)C0 * rows + R0;
@@ -323,47 +384,40 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   bool foreign = false;             /* tile holds values outside the HIMM set -> float view on global memory */
   const bool row_lo_ok = R0 + lane <= R1, row_hi_ok = R0 + lane + 32 <= R1;
 
-  for (int base = beg; base < end; base += LIST_CAP) {
-    const int chunk_end = min(base + LIST_CAP, end);
-    const BeamSeg* segs = a.segs + base;
-    const int n_chunk = chunk_end - base;
-
-    /* ---- filter: ordered list of the beams whose bounding box (or mark cell) touches the tile.  4 independent
-     * 24-byte loads per lane are in flight per round. ---- */
-    int n_list = 0; /* warp-uniform */
+  for (int chunk = 0; chunk < a.n_chunks; chunk++) {
+    const size_t t = ((size_t)blockIdx.y * a.n_chunks + chunk) * (size_t)(a.tiles_r * a.tiles_c) + blockIdx.x;
+    /* ---- this tile's beam set: 2048-bit mask written by the prep kernel; consume and clear it ---- */
+    uint32_t* mw = a.beam_masks + t * HIMM_MASK_WORDS;
+    const uint32_t w0 = mw[lane], w1 = mw[lane + 32];
+    if (__ballot_sync(0xffffffffu, (w0 | w1) != 0u) == 0u) continue;
+    if (w0) mw[lane] = 0u;
+    if (w1) mw[lane + 32] = 0u;
     unsigned long long need = 0ull;
-    for (int i0 = 0; i0 < n_chunk; i0 += 128) {
-      BeamSeg b4[4];
+    if (lane == 0) {
+      need = a.col_masks[t];
+      a.col_masks[t] = 0ull;
+    }
+    /* expand the mask into the ordered beam list: lane L owns words L and L+32 */
+    const int p0 = __popc(w0), p1 = __popc(w1);
+    int inc0 = p0, inc1 = p1;
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u + lane;
-        b4[u].r0 = -1;
-        b4[u].mr = -1;
-        if (i < n_chunk) b4[u] = segs[i];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const BeamSeg b = b4[u];
-        bool hit = false;
-        if (b.r0 >= 0 && max(b.r0, b.r1) >= R0 && min(b.r0, b.r1) <= R1) {
-          /* columns the beam may touch inside this tile (bounding box: conservative) */
-          const int ca = max(min(b.c0, b.c1), C0), cb = min(max(b.c0, b.c1), C1);
-          if (ca <= cb) {
-            hit = true;
-            need |= (~0ull >> (63 - (cb - ca))) << (ca - C0);
-          }
-        }
-        if (b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1) {
-          hit = true;
-          need |= 1ull << (b.mc - C0);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(i0 + 32 * u + lane);
-        n_list += __popc(bal);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u0 = __shfl_up_sync(0xffffffffu, inc0, o), u1 = __shfl_up_sync(0xffffffffu, inc1, o);
+      if (lane >= o) {
+        inc0 += u0;
+        inc1 += u1;
       }
     }
+    const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+    const int n_list = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
+    {
+      int pos = inc0 - p0;
+      for (uint32_t w = w0; w; w &= w - 1) list[pos++] = (uint16_t)(32 * lane + __ffs(w) - 1);
+      pos = tot0 + inc1 - p1;
+      for (uint32_t w = w1; w; w &= w - 1) list[pos++] = (uint16_t)(32 * (lane + 32) + __ffs(w) - 1);
+    }
     __syncwarp();
-    if (n_list == 0) continue;
+    const BeamSeg* segs = a.segs + beg + chunk * HIMM_CHUNK;
 
     if (!foreign) {
       /* ---- stage the newly needed columns: float -> code, 8 columns (16 loads per lane) in flight per round ---- */

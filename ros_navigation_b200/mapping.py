@@ -91,9 +91,9 @@ class DeviceGridMap:
         check(lib().b200nav_himm_update_batched(self.h, layer.encode(), samples.ctypes.data, offsets.ctypes.data,
                                                 ptr(bbox)), self.ctx.h)
 
-    def himm_update_batched_dev(self, layer, dev_samples, dev_offsets, total):
+    def himm_update_batched_dev(self, layer, dev_samples, dev_offsets, total, max_per_robot):
         check(lib().b200nav_himm_update_batched_dev(self.h, layer.encode(), ptr(dev_samples), ptr(dev_offsets),
-                                                    int(total)), self.ctx.h)
+                                                    int(total), int(max_per_robot)), self.ctx.h)
 
     def himm_last_stats(self):
         """(cell visits, marks, beams) of the last update (roofline accounting)."""

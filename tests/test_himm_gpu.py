@@ -206,7 +206,7 @@ def test_c4_full_size_properties(ctx):
         rng_, ang = w.cast(x, y, yaw, cfg["beams"], cfg["fov"], cfg["range_max"])
         s8, off = synth.samples_from_scan(x, y, yaw, rng_, ang, cfg["range_max"])
         torch.cuda.synchronize()
-        dg.himm_update_batched_dev("laser", s8, off, int(off[-1]))
+        dg.himm_update_batched_dev("laser", s8, off, int(off[-1]), cfg["beams"])
         ctx.synchronize()
         sn, offn = synth.samples_to_numpy(s8), off.cpu().numpy()
         for r in spots:
@@ -215,7 +215,7 @@ def test_c4_full_size_properties(ctx):
         assert_layers_equal(dg.download("laser", robot=r), layers[r], "c4 robot %d" % r)
     # invariants over all robots, checked on the device layer through torch (plumbing only)
     for _ in range(18):
-        dg.himm_update_batched_dev("laser", s8, off, int(off[-1]))
+        dg.himm_update_batched_dev("laser", s8, off, int(off[-1]), cfg["beams"])
     ctx.synchronize()
     for r in spots:
         for _ in range(18):
