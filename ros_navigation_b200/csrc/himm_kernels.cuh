@@ -193,35 +193,80 @@ struct HimmTileCfg {
  *   markCell(c)  = c <= 1 ? 4 : (c <= 16 ? c + 3 : c)         (NaN or 0 -> 30; <= 150 -> +30) */
 #define HIMM_CODE_NAN 0
 
+/* Small non-negative integers <-> float without I2F/F2I: float(0x4B000000 + k) == 8388608 + k exactly. */
+__device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B000000 + k) - 8388608.0f; }
+
 /* float -> code; returns 255 for a value outside the HIMM set */
 __device__ __forceinline__ unsigned himm_encode(float v) {
-  if (v != v) return HIMM_CODE_NAN;
-  const int c = __float2int_rn(v * 0.1f);
-  /* -0.0f compares equal to 0 but has another bit pattern: keep it out of the set so it round-trips */
-  return (c >= 0 && c <= 18 && (float)(c * 10) == v && __float_as_uint(v) != 0x80000000u) ? (unsigned)(c + 1) : 255u;
+  /* c = round(v/10) through the magic add; garbage for NaN / negative / huge inputs is rejected by the checks */
+  const int c = __float_as_int(v * 0.1f + 8388608.0f) - 0x4B000000;
+  const bool in_set = (unsigned)c <= 18u && small_int_to_float(c * 10) == v && __float_as_uint(v) != 0x80000000u;
+  /* -0.0f compares equal to 0 but has another bit pattern: it stays out of the set so that it round-trips */
+  return (v != v) ? (unsigned)HIMM_CODE_NAN : (in_set ? (unsigned)(c + 1) : 255u);
 }
 __device__ __forceinline__ float himm_decode(unsigned c) {
-  return c == HIMM_CODE_NAN ? __int_as_float(0x7fc00000) : (float)(int)(c * 10u - 10u);
+  return c == HIMM_CODE_NAN ? __int_as_float(0x7fc00000) : small_int_to_float((int)(c * 10u) - 10);
 }
 
-/* Tile views: the walk is written once against this interface. */
+/* Tile views: the walk is written once against this interface.
+ *   sensitive(off)   does the result of visiting this cell depend on how many beams visit it / in which order?
+ *                    (code <= 1, i.e. NaN or 0: any number of clears gives 0 -> not sensitive)
+ *   set_free(off)    result of >= 1 clears on a non-sensitive cell
+ *   clear_n / clear_seq   exact application of a group of visits */
+/* Shared-memory byte access through an explicit 32-bit shared address (a generic pointer would cost an address
+ * space conversion on every access of the hot loop). */
+__device__ __forceinline__ int lds_u8(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, int v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 struct CodeView { /* shared memory, one byte per cell */
-  uint8_t* p;
-  __device__ __forceinline__ void clear(int off, bool mark) const {
-    int c = max((int)p[off] - 1, 1);                 /* clearCell */
-    if (mark) c = (c <= 16) ? c + 3 : c;             /* markCell (c >= 1 here) */
-    p[off] = (uint8_t)c;
+  uint32_t base; /* shared-space address of the tile */
+  __device__ __forceinline__ bool sensitive(int off) const { return lds_u8(base + off) >= 2; }
+  __device__ __forceinline__ void set_free(int off) const { sts_u8(base + off, 1); }
+  __device__ __forceinline__ void clear_n(int off, int n, bool mark) const {
+    int c = max(lds_u8(base + off) - n, 1);
+    if (mark) c = (c <= 16) ? c + 3 : c;
+    sts_u8(base + off, c);
+  }
+  /* clears and marks of several beams on one cell, in lane order: lanes in `group`, those in `marks` also mark */
+  __device__ __forceinline__ void clear_seq(int off, unsigned group, unsigned marks) const {
+    int c = lds_u8(base + off);
+    while (group) {
+      const unsigned bit = group & (0u - group);
+      group ^= bit;
+      c = max(c - 1, 1);
+      if (marks & bit) c = (c <= 16) ? c + 3 : c;
+    }
+    sts_u8(base + off, c);
   }
   __device__ __forceinline__ void mark(int off) const {
-    const int c = p[off];
-    p[off] = (uint8_t)((c <= 1) ? 4 : ((c <= 16) ? c + 3 : c));
+    const int c = lds_u8(base + off);
+    sts_u8(base + off, (c <= 1) ? 4 : ((c <= 16) ? c + 3 : c));
   }
 };
 struct FloatView { /* global memory, in place (tiles with values outside the HIMM set) */
   volatile float* p;
-  __device__ __forceinline__ void clear(int off, bool mark) const {
-    float v = himm_clear(p[off]);
+  __device__ __forceinline__ bool sensitive(int) const { return true; }
+  __device__ __forceinline__ void set_free(int off) const { p[off] = 0.0f; }
+  __device__ __forceinline__ void clear_n(int off, int n, bool mark) const {
+    float v = p[off];
+    for (int i = 0; i < n; i++) v = himm_clear(v);
     if (mark) v = himm_mark(v);
+    p[off] = v;
+  }
+  __device__ __forceinline__ void clear_seq(int off, unsigned group, unsigned marks) const {
+    float v = p[off];
+    while (group) {
+      const unsigned bit = group & (0u - group);
+      group ^= bit;
+      v = himm_clear(v);
+      if (marks & bit) v = himm_mark(v);
+    }
     p[off] = v;
   }
   __device__ __forceinline__ void mark(int off) const { p[off] = himm_mark(p[off]); }
@@ -237,10 +282,8 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
    * first step inside.  Then one of two exact schedules:
    *  (fan)     all beams of the batch start in the SAME cell (a lidar scan).  A cell at step t of such a line has
    *            Chebyshev distance exactly t from that cell, so two beams can only share a cell at EQUAL step index.
-   *            Lane L walks its own beam, skewed so that at time tau it is at step tau - L: at any instant all lanes
-   *            are at different steps => different cells (no conflicts, no atomics), and a shared cell is reached in
-   *            lane order == sample order.  The +30 mark is applied by the same lane right after the clear of its
-   *            end cell.
+   *            Lane L walks its own beam and all lanes advance over t together, so all visits of a cell by this
+   *            batch fall into one iteration and are resolved there, in lane order == sample order (see below).
    *  (general) anything else (clipped rays, mixed origins, mark without a line): one beam at a time, the 32 lanes
    *            striding over its cells (a Bresenham line never visits a cell twice). */
   BeamSeg nb;
@@ -292,18 +335,32 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
     const int lr0 = __shfl_sync(0xffffffffu, my_r0, lead), lc0 = __shfl_sync(0xffffffffu, my_c0, lead);
     const bool lane_ok = !has_work || (my_len > 0 && my_r0 == lr0 && my_c0 == lc0 && (my_moff < 0 || mark_at_end));
     if (__all_sync(0xffffffffu, lane_ok)) {
-      /* ---- fan schedule (skewed): lane L is at step tau - L at time tau ---- */
-      const int first = (my_len > 0) ? my_t0 + lane : 0x7fffffff;
-      const int last = (my_len > 0) ? my_t0 + my_len - 1 + lane : -0x7fffffff;
-      const int tau0 = __reduce_min_sync(0xffffffffu, first), tau1 = __reduce_max_sync(0xffffffffu, last);
-      int off = my_off0, rem = my_rem0;
+      /* ---- fan schedule: all lanes advance together over the absolute step index t, so every visit this
+       * batch pays to a cell happens in ONE iteration.  Cells holding NaN or 0 end up 0 however many beams clear
+       * them, so an iteration in which no lane sees a larger value and no lane marks needs no coordination at
+       * all (the common case: free space).  Otherwise match.any groups the lanes by cell and the lowest lane of
+       * each group applies the group's clears and +30 marks in lane order == sample order. ---- */
+      const int first = (my_len > 0) ? my_t0 : 0x7fffffff;
       const unsigned span = (my_len > 0) ? (unsigned)(my_len - 1) : 0u;
-      const int mark_k = (my_moff >= 0) ? (int)span : -1; /* iteration (relative to `first`) that also marks */
-      int k = tau0 - first;                               /* my step relative to my first; negative = not yet */
-      if (my_len <= 0) k = -0x40000000;
-      for (int tau = tau0; tau <= tau1; tau++, k++) {
-        if ((unsigned)k <= span) {
-          view.clear(off, k == mark_k);
+      const int last = (my_len > 0) ? my_t0 + my_len - 1 : -0x7fffffff;
+      const int tmin = __reduce_min_sync(0xffffffffu, first), tmax = __reduce_max_sync(0xffffffffu, last);
+      int off = my_off0, rem = my_rem0;
+      const int mark_k = (my_moff >= 0) ? (int)span : -1; /* step (relative to `first`) that also marks */
+      int k = (my_len > 0) ? tmin - first : -0x40000000;
+      for (int t = tmin; t <= tmax; t++, k++) {
+        const bool on = (unsigned)k <= span;
+        const bool sens = on && (k == mark_k || view.sensitive(off));
+        if (!__any_sync(0xffffffffu, sens)) {
+          if (on) view.set_free(off);
+        } else {
+          const unsigned group = __match_any_sync(0xffffffffu, on ? off : -1 - lane);
+          const unsigned marks = __ballot_sync(0xffffffffu, on && k == mark_k) & group;
+          if (on && (group & ((1u << lane) - 1u)) == 0u) { /* lowest lane of the group */
+            if (marks == 0u) view.clear_n(off, __popc(group), false);
+            else view.clear_seq(off, group, marks);
+          }
+        }
+        if (on) {
           rem += my_add;
           off += my_dm;
           if (rem >= my_den) {
@@ -338,7 +395,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           const int r32 = x32 - q32 * den;
           const int step = 32 * dm + q32 * dn;
           for (int k = lane; k < len; k += 32) {
-            view.clear(off, false);
+            view.clear_n(off, 1, false);
             rem += r32;
             off += step;
             if (rem >= den) {
@@ -383,6 +440,8 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   unsigned long long loaded = 0ull; /* columns staged in shared memory (bit c = column C0+c) */
   bool foreign = false;             /* tile holds values outside the HIMM set -> float view on global memory */
   const bool row_lo_ok = R0 + lane <= R1, row_hi_ok = R0 + lane + 32 <= R1;
+  /* float4 path: every column segment of the tile is 16-byte aligned and a whole number of quads */
+  const bool vec_ok = (rows & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.layer) & 15) == 0);
 
   for (int chunk = 0; chunk < a.n_chunks; chunk++) {
     const size_t t = ((size_t)blockIdx.y * a.n_chunks + chunk) * (size_t)(a.tiles_r * a.tiles_c) + blockIdx.x;
@@ -420,35 +479,72 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
     const BeamSeg* segs = a.segs + beg + chunk * HIMM_CHUNK;
 
     if (!foreign) {
-      /* ---- stage the newly needed columns: float -> code, 8 columns (16 loads per lane) in flight per round ---- */
+      /* ---- stage the newly needed columns: float -> code ---- */
       unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)need), hi = __reduce_or_sync(0xffffffffu, (unsigned)(need >> 32));
       unsigned long long m = (((unsigned long long)hi << 32) | lo) & ~loaded;
       loaded |= m;
       unsigned bad = 0;
-      while (m) {
-        int cidx[8];
-        float v0[8], v1[8];
+      if (vec_ok) {
+        /* 16 lanes x float4 cover one column (64 rows): two columns per warp-wide LDG.128, 4 in flight per lane */
+        const int half = lane >> 4, quad = lane & 15;
+        while (m) {
+          int cidx[4];
+          float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          cidx[u] = m ? __ffsll((long long)m) - 1 : -1;
-          if (m) m &= m - 1;
-        }
+          for (int u = 0; u < 4; u++) {
+            int ca = -1, cb = -1;
+            if (m) {
+              ca = __ffsll((long long)m) - 1;
+              m &= m - 1;
+            }
+            if (m) {
+              cb = __ffsll((long long)m) - 1;
+              m &= m - 1;
+            }
+            cidx[u] = half ? cb : ca;
+          }
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          v0[u] = v1[u] = 0.f;
-          if (cidx[u] >= 0) {
-            const float* src = gtile + (size_t)cidx[u] * rows + lane;
-            if (row_lo_ok) v0[u] = src[0];
-            if (row_hi_ok) v1[u] = src[32];
+          for (int u = 0; u < 4; u++) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cidx[u] >= 0 && R0 + 4 * quad <= R1)
+              v[u] = *reinterpret_cast<const float4*>(gtile + (size_t)cidx[u] * rows + 4 * quad);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (cidx[u] >= 0) {
+              const unsigned c0 = himm_encode(v[u].x), c1 = himm_encode(v[u].y), c2 = himm_encode(v[u].z),
+                             c3 = himm_encode(v[u].w);
+              if (R0 + 4 * quad <= R1) bad |= ((c0 | c1 | c2 | c3) == 255u);
+              *reinterpret_cast<uint32_t*>(tile + cidx[u] * Cfg::kPitch + 4 * quad) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+            }
           }
         }
+      } else {
+        while (m) {
+          int cidx[8];
+          float v0[8], v1[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          if (cidx[u] >= 0) {
-            const unsigned c0 = himm_encode(v0[u]), c1 = himm_encode(v1[u]);
-            bad |= (row_lo_ok && c0 == 255u) || (row_hi_ok && c1 == 255u);
-            tile[cidx[u] * Cfg::kPitch + lane] = (uint8_t)c0;
-            tile[cidx[u] * Cfg::kPitch + lane + 32] = (uint8_t)c1;
+          for (int u = 0; u < 8; u++) {
+            cidx[u] = m ? __ffsll((long long)m) - 1 : -1;
+            if (m) m &= m - 1;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            v0[u] = v1[u] = 0.f;
+            if (cidx[u] >= 0) {
+              const float* src = gtile + (size_t)cidx[u] * rows + lane;
+              if (row_lo_ok) v0[u] = src[0];
+              if (row_hi_ok) v1[u] = src[32];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            if (cidx[u] >= 0) {
+              const unsigned c0 = himm_encode(v0[u]), c1 = himm_encode(v1[u]);
+              bad |= (row_lo_ok && c0 == 255u) || (row_hi_ok && c1 == 255u);
+              tile[cidx[u] * Cfg::kPitch + lane] = (uint8_t)c0;
+              tile[cidx[u] * Cfg::kPitch + lane + 32] = (uint8_t)c1;
+            }
           }
         }
       }
@@ -481,7 +577,7 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
 
     /* ---- apply the beams in sample order ---- */
     if (!foreign)
-      himm_apply_list(CodeView{tile}, Cfg::kPitch, segs, list, n_list, R0, R1, C0, C1, lane);
+      himm_apply_list(CodeView{(uint32_t)__cvta_generic_to_shared(tile)}, Cfg::kPitch, segs, list, n_list, R0, R1, C0, C1, lane);
     else
       himm_apply_list(FloatView{gtile}, rows, segs, list, n_list, R0, R1, C0, C1, lane);
     __syncwarp(); /* the list is rewritten by the next chunk */
@@ -490,13 +586,35 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   /* ---- write back the staged (== possibly touched) columns: code -> float, coalesced 256-byte segments ---- */
   {
     unsigned long long m = loaded;
-    while (m) {
-      const int c = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      float* dst = gtile + (size_t)c * rows + lane;
-      const unsigned c0 = tile[c * Cfg::kPitch + lane], c1 = tile[c * Cfg::kPitch + lane + 32];
-      if (row_lo_ok) dst[0] = himm_decode(c0);
-      if (row_hi_ok) dst[32] = himm_decode(c1);
+    if (vec_ok) {
+      const int half = lane >> 4, quad = lane & 15;
+      while (m) {
+        int ca = __ffsll((long long)m) - 1, cb = -1;
+        m &= m - 1;
+        if (m) {
+          cb = __ffsll((long long)m) - 1;
+          m &= m - 1;
+        }
+        const int c = half ? cb : ca;
+        if (c >= 0 && R0 + 4 * quad <= R1) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(tile + c * Cfg::kPitch + 4 * quad);
+          float4 o;
+          o.x = himm_decode(w & 0xffu);
+          o.y = himm_decode((w >> 8) & 0xffu);
+          o.z = himm_decode((w >> 16) & 0xffu);
+          o.w = himm_decode(w >> 24);
+          *reinterpret_cast<float4*>(gtile + (size_t)c * rows + 4 * quad) = o;
+        }
+      }
+    } else {
+      while (m) {
+        const int c = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        float* dst = gtile + (size_t)c * rows + lane;
+        const unsigned c0 = tile[c * Cfg::kPitch + lane], c1 = tile[c * Cfg::kPitch + lane + 32];
+        if (row_lo_ok) dst[0] = himm_decode(c0);
+        if (row_hi_ok) dst[32] = himm_decode(c1);
+      }
     }
   }
 }
