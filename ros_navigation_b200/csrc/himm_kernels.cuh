@@ -344,12 +344,12 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
       const unsigned span = (my_len > 0) ? (unsigned)(my_len - 1) : 0u;
       const int last = (my_len > 0) ? my_t0 + my_len - 1 : -0x7fffffff;
       const int tmin = __reduce_min_sync(0xffffffffu, first), tmax = __reduce_max_sync(0xffffffffu, last);
-      int off = my_off0, rem = my_rem0;
+      int off = my_off0, rem = my_rem0; /* `off` always addresses a cell of this tile, also while the lane idles */
       const int mark_k = (my_moff >= 0) ? (int)span : -1; /* step (relative to `first`) that also marks */
       int k = (my_len > 0) ? tmin - first : -0x40000000;
-      for (int t = tmin; t <= tmax; t++, k++) {
+      for (int it = tmax - tmin; it >= 0; it--, k++) {
         const bool on = (unsigned)k <= span;
-        const bool sens = on && (k == mark_k || view.sensitive(off));
+        const bool sens = on && (view.sensitive(off) || k == mark_k);
         if (!__any_sync(0xffffffffu, sens)) {
           if (on) view.set_free(off);
         } else {
@@ -360,7 +360,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
             else view.clear_seq(off, group, marks);
           }
         }
-        if (on) {
+        if ((unsigned)k < span) { /* advance to my next cell (stay on the last one) */
           rem += my_add;
           off += my_dm;
           if (rem >= my_den) {
@@ -421,6 +421,10 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   extern __shared__ __align__(16) unsigned char himm_smem_raw[];
   uint8_t* tile = himm_smem_raw;
   uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + Cfg::kTileBytes);
+
+  /* shared-space address of the tile, pinned in a register (keeps the address computation out of the hot loop) */
+  uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
+  asm volatile("mov.u32 %0, %0;" : "+r"(tile_saddr));
 
   const int lane = threadIdx.x;
   const int robot = a.robot0 + blockIdx.y;
@@ -487,38 +491,46 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
       if (vec_ok) {
         /* 16 lanes x float4 cover one column (64 rows): two columns per warp-wide LDG.128, 4 in flight per lane */
         const int half = lane >> 4, quad = lane & 15;
-        while (m) {
-          int cidx[4];
-          float4 v[4];
+        const bool quad_ok = R0 + 4 * quad <= R1;
+        const uint32_t my_saddr = tile_saddr + 4 * quad;
+        const float* my_g = gtile + 4 * quad;
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            int ca = -1, cb = -1;
-            if (m) {
-              ca = __ffsll((long long)m) - 1;
-              m &= m - 1;
+        for (int h = 0; h < 2; h++) {
+          uint32_t w32 = h ? (uint32_t)(m >> 32) : (uint32_t)m;
+          while (w32) {
+            int cidx[4];
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              int ca = -1, cb = -1;
+              if (w32) {
+                ca = __ffs(w32) - 1 + 32 * h;
+                w32 &= w32 - 1;
+              }
+              if (w32) {
+                cb = __ffs(w32) - 1 + 32 * h;
+                w32 &= w32 - 1;
+              }
+              cidx[u] = quad_ok ? (half ? cb : ca) : -1;
             }
-            if (m) {
-              cb = __ffsll((long long)m) - 1;
-              m &= m - 1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (cidx[u] >= 0) v[u] = *reinterpret_cast<const float4*>(my_g + (unsigned)(cidx[u] * rows));
             }
-            cidx[u] = half ? cb : ca;
-          }
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cidx[u] >= 0 && R0 + 4 * quad <= R1)
-              v[u] = *reinterpret_cast<const float4*>(gtile + (size_t)cidx[u] * rows + 4 * quad);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            if (cidx[u] >= 0) {
-              const unsigned c0 = himm_encode(v[u].x), c1 = himm_encode(v[u].y), c2 = himm_encode(v[u].z),
-                             c3 = himm_encode(v[u].w);
-              if (R0 + 4 * quad <= R1) bad |= ((c0 | c1 | c2 | c3) == 255u);
-              *reinterpret_cast<uint32_t*>(tile + cidx[u] * Cfg::kPitch + 4 * quad) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+            for (int u = 0; u < 4; u++) {
+              if (cidx[u] >= 0) {
+                const unsigned c0 = himm_encode(v[u].x), c1 = himm_encode(v[u].y), c2 = himm_encode(v[u].z),
+                               c3 = himm_encode(v[u].w);
+                bad |= ((c0 | c1 | c2 | c3) == 255u);
+                const uint32_t packed = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_saddr + cidx[u] * Cfg::kPitch), "r"(packed) : "memory");
+              }
             }
           }
         }
+        m = 0ull;
       } else {
         while (m) {
           int cidx[8];
@@ -577,7 +589,7 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
 
     /* ---- apply the beams in sample order ---- */
     if (!foreign)
-      himm_apply_list(CodeView{(uint32_t)__cvta_generic_to_shared(tile)}, Cfg::kPitch, segs, list, n_list, R0, R1, C0, C1, lane);
+      himm_apply_list(CodeView{tile_saddr}, Cfg::kPitch, segs, list, n_list, R0, R1, C0, C1, lane);
     else
       himm_apply_list(FloatView{gtile}, rows, segs, list, n_list, R0, R1, C0, C1, lane);
     __syncwarp(); /* the list is rewritten by the next chunk */
@@ -588,22 +600,31 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
     unsigned long long m = loaded;
     if (vec_ok) {
       const int half = lane >> 4, quad = lane & 15;
-      while (m) {
-        int ca = __ffsll((long long)m) - 1, cb = -1;
-        m &= m - 1;
-        if (m) {
-          cb = __ffsll((long long)m) - 1;
-          m &= m - 1;
-        }
-        const int c = half ? cb : ca;
-        if (c >= 0 && R0 + 4 * quad <= R1) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(tile + c * Cfg::kPitch + 4 * quad);
-          float4 o;
-          o.x = himm_decode(w & 0xffu);
-          o.y = himm_decode((w >> 8) & 0xffu);
-          o.z = himm_decode((w >> 16) & 0xffu);
-          o.w = himm_decode(w >> 24);
-          *reinterpret_cast<float4*>(gtile + (size_t)c * rows + 4 * quad) = o;
+      const bool quad_ok = R0 + 4 * quad <= R1;
+      const uint32_t my_saddr = tile_saddr + 4 * quad;
+      float* my_g = gtile + 4 * quad;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint32_t w32 = h ? (uint32_t)(m >> 32) : (uint32_t)m;
+        while (w32) {
+          int ca = __ffs(w32) - 1, cb = -1;
+          w32 &= w32 - 1;
+          if (w32) {
+            cb = __ffs(w32) - 1;
+            w32 &= w32 - 1;
+          }
+          const int c = (half ? cb : ca);
+          if (c >= 0 && quad_ok) {
+            const int cc = c + 32 * h;
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(my_saddr + cc * Cfg::kPitch) : "memory");
+            float4 o;
+            o.x = himm_decode(w & 0xffu);
+            o.y = himm_decode((w >> 8) & 0xffu);
+            o.z = himm_decode((w >> 16) & 0xffu);
+            o.w = himm_decode(w >> 24);
+            *reinterpret_cast<float4*>(my_g + (unsigned)(cc * rows)) = o;
+          }
         }
       }
     } else {
