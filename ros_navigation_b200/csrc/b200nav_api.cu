@@ -216,9 +216,9 @@ constexpr int kSub = HIMM_TILE, kListCap = HIMM_CHUNK;
 using TileCfg = HimmTileCfg<kSub, kListCap>;
 
 /* Binning scratch: grow-only, kept all-zero between updates (the tile kernel clears what it consumes). */
-int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total) {
+int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words) {
   b200nav_ctx* ctx = g->ctx;
-  const size_t mb = n_tiles_total * HIMM_MASK_WORDS * sizeof(uint32_t), cb = n_tiles_total * sizeof(unsigned long long);
+  const size_t mb = n_tiles_total * (size_t)mask_words * sizeof(uint32_t), cb = n_tiles_total * sizeof(unsigned long long);
   if (mb > g->beam_masks.cap) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, g->beam_masks.reserve(mb));
@@ -254,9 +254,11 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   a.total = total;
   a.tiles_r = (g->dims.rows + TileCfg::kTileR - 1) / TileCfg::kTileR;
   a.tiles_c = (g->dims.cols + TileCfg::kTileC - 1) / TileCfg::kTileC;
-  a.n_chunks = std::max(1, (max_per_robot + HIMM_CHUNK - 1) / HIMM_CHUNK);
+  a.chunk_beams = std::min(HIMM_CHUNK, std::max(32, (max_per_robot + 31) & ~31));
+  a.mask_words = a.chunk_beams / 32;
+  a.n_chunks = std::max(1, (max_per_robot + a.chunk_beams - 1) / a.chunk_beams);
   const size_t n_tiles_total = (size_t)n_active * a.n_chunks * a.tiles_r * a.tiles_c;
-  int rc = himm_reserve_masks(g, n_tiles_total);
+  int rc = himm_reserve_masks(g, n_tiles_total, a.mask_words);
   if (rc) return rc;
   a.beam_masks = static_cast<uint32_t*>(g->beam_masks.p);
   a.col_masks = static_cast<unsigned long long*>(g->col_masks.p);
@@ -272,7 +274,8 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   dim3 grid((unsigned)(a.tiles_r * a.tiles_c), (unsigned)n_active);
   {
     ProfScope ps(ctx, PROF_HIMM_TILE);
-    kern<<<grid, TileCfg::kThreads, TileCfg::kSmemBytes, ctx->stream>>>(a);
+    const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
+    kern<<<grid, TileCfg::kThreads, smem, ctx->stream>>>(a);
   }
   return check_launch(ctx, "himm_tile_kernel");
 }

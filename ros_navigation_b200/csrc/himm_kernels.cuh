@@ -30,7 +30,7 @@
 namespace b200nav {
 
 #define HIMM_TILE 64        /* tile edge in cells (one warp owns one tile)                                  */
-#define HIMM_CHUNK 2048     /* beams per chunk: one tile's beam set is a 2048-bit mask (64 words)           */
+#define HIMM_CHUNK 2048     /* max beams per chunk: a tile's beam set is a bit mask of <= 2048 bits          */
 #define HIMM_MASK_WORDS (HIMM_CHUNK / 32)
 
 struct HimmArgs {
@@ -52,12 +52,14 @@ struct HimmArgs {
   int total;                      /* total samples                                */
   int tiles_r, tiles_c;           /* tiles per grid                               */
   int n_chunks;                   /* chunks per robot                             */
+  int chunk_beams;                /* beams per chunk: multiple of 32, <= HIMM_CHUNK */
+  int mask_words;                 /* chunk_beams / 32                              */
 };
 
 __device__ __forceinline__ void himm_bin_tile(const HimmArgs& a, size_t rc_base, int tr, int tc, int word, uint32_t bit,
                                               int col_lo, int col_hi) {
   const size_t t = rc_base + (size_t)(tc * a.tiles_r + tr);
-  atomicOr(&a.beam_masks[t * HIMM_MASK_WORDS + word], bit);
+  atomicOr(&a.beam_masks[t * a.mask_words + word], bit);
   const int c0 = max(col_lo - tc * HIMM_TILE, 0), c1 = min(col_hi - tc * HIMM_TILE, HIMM_TILE - 1);
   if (c0 <= c1) atomicOr(&a.col_masks[t], (~0ull >> (63 - (c1 - c0))) << c0);
 }
@@ -91,12 +93,12 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
   a.segs[i] = b;
 
   const int k = i - beg; /* index of the beam within its robot */
-  const int chunk = k / HIMM_CHUNK;
+  const int chunk = k / a.chunk_beams;
   if (chunk >= a.n_chunks) {
     *a.error_flag = 1;
     return;
   }
-  const int word = (k % HIMM_CHUNK) >> 5;
+  const int word = (k - chunk * a.chunk_beams) >> 5;
   const uint32_t bit = 1u << (k & 31);
   const size_t rc_base = ((size_t)rel * a.n_chunks + chunk) * (size_t)(a.tiles_r * a.tiles_c);
 
@@ -347,20 +349,40 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
       int off = my_off0, rem = my_rem0; /* `off` always addresses a cell of this tile, also while the lane idles */
       const int mark_k = (my_moff >= 0) ? (int)span : -1; /* step (relative to `first`) that also marks */
       int k = (my_len > 0) ? tmin - first : -0x40000000;
-      for (int it = tmax - tmin; it >= 0; it--, k++) {
-        const bool on = (unsigned)k <= span;
-        const bool sens = on && (view.sensitive(off) || k == mark_k);
-        if (!__any_sync(0xffffffffu, sens)) {
-          if (on) view.set_free(off);
-        } else {
-          const unsigned group = __match_any_sync(0xffffffffu, on ? off : -1 - lane);
-          const unsigned marks = __ballot_sync(0xffffffffu, on && k == mark_k) & group;
-          if (on && (group & ((1u << lane) - 1u)) == 0u) { /* lowest lane of the group */
-            if (marks == 0u) view.clear_n(off, __popc(group), false);
-            else view.clear_seq(off, group, marks);
+      /* exact application of one ring (all lanes at the same step): group lanes by cell, lowest lane applies */
+      auto ring_exact = [&](bool on, int o, bool marking) {
+        const unsigned group = __match_any_sync(0xffffffffu, on ? o : -1 - lane);
+        const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
+        if (on && (group & ((1u << lane) - 1u)) == 0u) {
+          if (marks == 0u) view.clear_n(o, __popc(group), false);
+          else view.clear_seq(o, group, marks);
+        }
+      };
+      /* two steps (two disjoint rings of cells) per iteration */
+      for (int it = tmax - tmin; it >= 0; it -= 2, k += 2) {
+        const bool onA = (unsigned)k <= span, onB = (unsigned)(k + 1) <= span;
+        int offB = off, remB = rem;
+        if ((unsigned)k < span) { /* my next cell (stay on the last one) */
+          remB += my_add;
+          offB += my_dm;
+          if (remB >= my_den) {
+            remB -= my_den;
+            offB += my_dn;
           }
         }
-        if ((unsigned)k < span) { /* advance to my next cell (stay on the last one) */
+        const bool sens = (onA && (view.sensitive(off) || k == mark_k)) ||
+                          (onB && (view.sensitive(offB) || k + 1 == mark_k));
+        if (!__any_sync(0xffffffffu, sens)) {
+          if (onA) view.set_free(off);
+          if (onB) view.set_free(offB);
+        } else {
+          ring_exact(onA, off, k == mark_k);
+          __syncwarp();
+          ring_exact(onB, offB, k + 1 == mark_k);
+        }
+        off = offB;
+        rem = remB;
+        if ((unsigned)(k + 1) < span) {
           rem += my_add;
           off += my_dm;
           if (rem >= my_den) {
@@ -420,7 +442,7 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   static_assert(SUB == HIMM_TILE && LIST_CAP == HIMM_CHUNK, "tile / chunk constants");
   extern __shared__ __align__(16) unsigned char himm_smem_raw[];
   uint8_t* tile = himm_smem_raw;
-  uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + Cfg::kTileBytes);
+  uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + Cfg::kTileBytes); /* a.chunk_beams entries */
 
   /* shared-space address of the tile, pinned in a register (keeps the address computation out of the hot loop) */
   uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
@@ -450,8 +472,8 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   for (int chunk = 0; chunk < a.n_chunks; chunk++) {
     const size_t t = ((size_t)blockIdx.y * a.n_chunks + chunk) * (size_t)(a.tiles_r * a.tiles_c) + blockIdx.x;
     /* ---- this tile's beam set: 2048-bit mask written by the prep kernel; consume and clear it ---- */
-    uint32_t* mw = a.beam_masks + t * HIMM_MASK_WORDS;
-    const uint32_t w0 = mw[lane], w1 = mw[lane + 32];
+    uint32_t* mw = a.beam_masks + t * a.mask_words;
+    const uint32_t w0 = (lane < a.mask_words) ? mw[lane] : 0u, w1 = (lane + 32 < a.mask_words) ? mw[lane + 32] : 0u;
     if (__ballot_sync(0xffffffffu, (w0 | w1) != 0u) == 0u) continue;
     if (w0) mw[lane] = 0u;
     if (w1) mw[lane + 32] = 0u;
@@ -480,7 +502,7 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
       for (uint32_t w = w1; w; w &= w - 1) list[pos++] = (uint16_t)(32 * (lane + 32) + __ffs(w) - 1);
     }
     __syncwarp();
-    const BeamSeg* segs = a.segs + beg + chunk * HIMM_CHUNK;
+    const BeamSeg* segs = a.segs + beg + chunk * a.chunk_beams;
 
     if (!foreign) {
       /* ---- stage the newly needed columns: float -> code ---- */
