@@ -115,6 +115,8 @@ B200_HD void limit_position_to_range(double& px, double& py, double lx, double l
  * the running sum is part of the reference result).  max_steps bounds the loop for hostile input. */
 B200_HD bool clip_into_map(const GridDims& d, const RobotGeom& g, double sx, double sy, double ex, double ey, int& r,
                            int& c) {
+  /* Common case first: the end is inside the map and the direction (sqrt + two divisions) is never needed. */
+  if (grid_index(d, g, sx, sy, r, c)) return true;
   double nx = sx, ny = sy;
   double dx = ex - sx, dy = ey - sy;
   const double z = dx * dx + dy * dy;
@@ -124,12 +126,12 @@ B200_HD bool clip_into_map(const GridDims& d, const RobotGeom& g, double sx, dou
     dy = dy / n;
   }
   const double step = d.res - B200NAV_DBL_EPSILON;
-  while (!grid_index(d, g, nx, ny, r, c)) {
+  do {
     nx += step * dx;
     ny += step * dy;
     const double qx = ex - nx, qy = ey - ny;
     if (!(sqrt(qx * qx + qy * qy) >= step)) return false; /* also ends the loop on NaN */
-  }
+  } while (!grid_index(d, g, nx, ny, r, c));
   return true;
 }
 
@@ -150,8 +152,13 @@ B200_HD BeamSeg make_beam(const GridDims& d, const RobotGeom& g, double sx, doub
     b.c1 = c1;
   }
   if (!clear_end) {
+    /* mark cell = index(end).  When the line exists its last cell already is index(end) if the end is inside
+     * the map (the clip of the end returns immediately); only re-derive it otherwise. */
     int mr, mc;
-    if (grid_index(d, g, ex, ey, mr, mc)) {
+    if (b.r0 >= 0 && within_map(ex, ey, d.len_x, d.len_y, g.pos_x, g.pos_y)) {
+      b.mr = b.r1;
+      b.mc = b.c1;
+    } else if (grid_index(d, g, ex, ey, mr, mc)) {
       b.mr = mr;
       b.mc = mc;
     }

@@ -77,12 +77,23 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
     rel = 0;
     beg = 0;
   } else {
-    /* last r with offsets[r] <= i */
-    int lo = 0, hi = a.n_active;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(&a.offsets[mid]) <= i) lo = mid;
-      else hi = mid;
+    /* robot of beam i = last r with offsets[r] <= i.  One binary search per warp (lane 0, for the warp's first
+     * beam), then every lane walks forward from there: consecutive beams belong to the same or the next robots. */
+    const int lane = threadIdx.x & 31;
+    int lo = 0;
+    if (lane == 0) {
+      int hi = a.n_active;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&a.offsets[mid]) <= i) lo = mid;
+        else hi = mid;
+      }
+    }
+    lo = __shfl_sync(__activemask(), lo, 0);
+    int nxt = __ldg(&a.offsets[lo + 1]);
+    while (nxt <= i && lo + 1 < a.n_active) {
+      lo++;
+      nxt = __ldg(&a.offsets[lo + 1]);
     }
     rel = lo;
     beg = __ldg(&a.offsets[lo]);

@@ -1,0 +1,111 @@
+"""GPU: the C++ drop-in classes (include/b200nav_shim.hpp) driven like the reference node, and the 'next' rows of
+SURVEY section 8f that are already built: GridMap::move on the device and toOccupancyGrid."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import assert_layers_equal, lidar_samples
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ros_navigation_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def test_cpp_shim_matches_reference(tmp_path):
+    """Compiles tests/cpp/shim_check.cpp against the shim header + libb200nav.so and runs it."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref missing")
+    from ros_navigation_b200 import capi
+    O.lib()
+    exe = str(tmp_path / "shim_check")
+    cmd = ["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/cpp/shim_check.cpp"),
+           "-I" + os.path.join(ROOT, "include"), capi.LIB_PATH, O.LIB_PATH, O.REF_PATH,
+           "-Wl,-rpath," + os.path.dirname(capi.LIB_PATH), "-Wl,-rpath," + os.path.dirname(O.LIB_PATH),
+           "-Wl,-rpath," + os.path.dirname(O.REF_PATH), "-lpthread"]
+    subprocess.run(cmd, check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+def test_moving_map_scenario(ctx):
+    """mapTest_vfh / mapTest_graph: a 4 m map that follows the robot (MapProvider::loopMoveMap,
+    move_control/src/map_provider.cpp:177-188 -> GridMap::move, grid_map_core/src/GridMap.cpp:346-412), interleaved
+    with HIMM updates and VFH+ window reads across the circular-buffer seam."""
+    from ros_navigation_b200 import VFH, DeviceGridMap
+    rng = np.random.default_rng(11)
+    g = O.make_geom(4.0, 4.0, 0.05)
+    dg = DeviceGridMap(ctx, (4.0, 4.0), 0.05, layers=("master", "laser"))
+    laser, master = O.new_layer(g), O.new_layer(g)
+    v = VFH(ctx)
+    x = y = 0.0
+    for step in range(40):
+        x += rng.uniform(-0.12, 0.3)
+        y += rng.uniform(-0.2, 0.15)
+        if step % 2 == 0:
+            moved_o = O.move(g, [laser, master], x, y)
+            moved_d = dg.move((x, y))
+            assert moved_o == moved_d
+            (px, py), (s0, s1) = dg.get_geometry()
+            assert (px, py, s0, s1) == (g.pos_x, g.pos_y, g.start0, g.start1)
+        s = lidar_samples(rng, g, (x, y), 360, 0.2, 2.6, clear_frac=0.05)
+        O.himm_update(g, laser, s)
+        master[:] = laser
+        dg.himm_update("laser", s)
+        dg.copy_layer("master", "laser")
+        yaw = rng.uniform(-np.pi, np.pi)
+        want = O.ranges_from_submap(g, master, x, y, yaw)
+        v.update_from_grid(dg, "master", VFH.make_input(x=x, y=y, yaw=yaw))
+        assert np.array_equal(v.ranges()[:, 0], want[:, 0]), "step %d" % step
+    assert_layers_equal(dg.download("laser"), laser, "laser after moves")
+    assert_layers_equal(dg.download("master"), master, "master after moves")
+    # large jump: the whole map is dropped
+    assert O.move(g, [laser, master], x + 10.0, y - 7.0) == dg.move((x + 10.0, y - 7.0))
+    assert_layers_equal(dg.download("laser"), laser, "after jump")
+    v.close()
+    dg.close()
+
+
+def test_to_occupancy_grid(ctx):
+    """GridMapRosConverter::toOccupancyGrid (grid_map_ros/src/GridMapRosConverter.cpp:251-287) as MapProvider
+    publishes it (map_provider.cpp:207-214: layer master, 0..255)."""
+    from ros_navigation_b200 import DeviceGridMap
+    rng = np.random.default_rng(12)
+    for start in [(0, 0), (13, 57)]:
+        g = O.make_geom(6.5, 4.0, 0.05, 1.0, -2.0, start)
+        dg = DeviceGridMap(ctx, (6.5, 4.0), 0.05, (1.0, -2.0), layers=("master",))
+        dg.set_geometry(0, (1.0, -2.0), start)
+        layer = O.new_layer(g)
+        m = rng.random(layer.shape)
+        layer[m < 0.5] = rng.choice(np.arange(0, 190, 10.0), (m < 0.5).sum())
+        layer[(m >= 0.5) & (m < 0.55)] = -5.0
+        layer[(m >= 0.55) & (m < 0.6)] = 300.0
+        dg.upload("master", layer)
+        assert np.array_equal(dg.to_occupancy("master", 0.0, 255.0), O.to_occupancy(g, layer, 0.0, 255.0))
+        dg.close()
+
+
+def test_error_paths(ctx):
+    """Error behaviour of the C ABI: unknown layer, bad robot index, bad arguments -> negative codes, no crash."""
+    from ros_navigation_b200 import DeviceGridMap, capi
+    dg = DeviceGridMap(ctx, (4.0, 4.0), 0.05, layers=("master",))
+    s = np.zeros(4, capi.SAMPLE_DTYPE)
+    with pytest.raises(capi.B200NavError) as e:
+        dg.himm_update("nope", s)
+    assert e.value.code == capi.ENOLAYER
+    with pytest.raises(capi.B200NavError) as e:
+        dg.himm_update("master", s, robot=3)
+    assert e.value.code == capi.EINVAL
+    with pytest.raises(capi.B200NavError) as e:
+        DeviceGridMap(ctx, (4000.0, 4.0), 0.05)
+    assert e.value.code == capi.ERANGE
+    dg.close()
