@@ -6,9 +6,9 @@
 A step = one cycle of the batched perception-to-steering path: every robot fuses ONE laser scan into its HIMM grid
 (b200nav_himm_update_batched*) and takes ONE VFH+ decision from the window of that grid
 (b200nav_vfh_update_batched*); with N > 1 ranks the per-robot 16-byte steering commands are all-gathered (NCCL).
-Default workload = BASELINE config 4 ("batched 1024 independent robots, each a 512x512 grid and 1080-beam scans,
-sharded across 1/2/4/8 B200"): the 1024 robots are block-partitioned over the ranks (strong scaling, no data-path
-collective).  Inputs are synthetic (ros_navigation_b200/synth.py), pre-staged in HBM for `value` and in pinned host
+Default workload = BASELINE config 4 ("batched 1024 independent robots, each a 512x512 grid and 1080-beam scans"):
+robots are block-partitioned over the ranks with no data-path collective.  --scaling weak (default) gives every GPU
+the configuration's 1024 robots (N x 1024 in total); --scaling strong splits the 1024 robots over the N GPUs.  Inputs are synthetic (ros_navigation_b200/synth.py), pre-staged in HBM for `value` and in pinned host
 memory for `e2e`.  L2 is flushed between timed steps; every step is timed with CUDA events on the launching stream.
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
@@ -41,10 +41,8 @@ def log(*a):
 # workload construction (shared by both arms)
 # ----------------------------------------------------------------------------------------------------------------
 def local_robot_range(total, rank, world):
-    per = total // world
-    rem = total % world
-    lo = rank * per + min(rank, rem)
-    return lo, lo + per + (1 if rank < rem else 0)
+    from ros_navigation_b200.dist import partition
+    return partition(total, rank, world)
 
 
 class Cycles:
@@ -211,8 +209,8 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32 cells / f64 geometry", "data": "synthetic",
-        "config": workload_config(args.workload, world, args.robots or arm.cfg["robots"]),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 cells / f64 geometry", "data": "synthetic",
+        "config": workload_config(args.workload, world, (args.robots or arm.cfg["robots"]) * (world if args.scaling == "weak" else 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -235,7 +233,8 @@ def workload_config(name, world, robots_total):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
 class GpuArm:
-    def __init__(self, cfg_name, lo, hi, device, stream, world):
+    def __init__(self, cfg_name, lo, hi, device, stream, world, robots_total=None):
+        robots_total = robots_total or (hi - lo)
         import torch
         from ros_navigation_b200 import VFH, DeviceGridMap, VfhParams, capi
         self.torch = torch
@@ -248,8 +247,10 @@ class GpuArm:
         self.grid.alias("master", "laser")  # map_["master"] = map_["laser"] without the copy
         self.vfh = VFH(self.ctx, VfhParams(window_diameter=cfg["window"], cell_size=cfg["cell"],
                                            submap_length=cfg["submap"]), n_robots=self.n)
-        self.cmd = torch.zeros(self.n, 16, dtype=torch.uint8, device=device)
-        self.gathered = torch.zeros(world * self.n, 16, dtype=torch.uint8, device=device) if world > 1 else None
+        from ros_navigation_b200.dist import CommandExchange
+        self.exchange = CommandExchange(robots_total, device) if world > 1 else None
+        self.cmd = self.exchange.local if self.exchange else torch.zeros(self.n, 16, dtype=torch.uint8, device=device)
+        self.gathered = self.exchange.table if self.exchange else None
         self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
         self.flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=device)
         # pinned host copies for the end-to-end path
@@ -257,11 +258,11 @@ class GpuArm:
         self.h_offsets = [o.cpu().pin_memory() for o in self.cyc.offsets]
         self.h_inputs = [i.cpu().pin_memory() for i in self.cyc.inputs]
         self.d_inputs_e2e = torch.zeros_like(self.cyc.inputs[0])
-        self.h_cmd = torch.zeros((world * self.n if world > 1 else self.n), 16, dtype=torch.uint8).pin_memory()
+        self.h_cmd = torch.zeros((robots_total if world > 1 else self.n), 16, dtype=torch.uint8).pin_memory()
 
     def all_gather(self):
-        if self.gathered is not None:
-            self.torch.distributed.all_gather_into_tensor(self.gathered.view(-1), self.cmd.view(-1))
+        if self.exchange is not None:
+            self.exchange.gather()
 
     def step_dev(self, i):
         c = i % N_CYCLES
@@ -322,7 +323,10 @@ def run_gpu_arm(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     cfg = synth.CONFIGS[args.workload]
-    robots_total = args.robots or cfg["robots"]
+    per_config = args.robots or cfg["robots"]
+    # weak scaling (default): every GPU carries the configuration's full robot count; strong: the configuration's
+    # robots are split over the GPUs ("1024 robots sharded across 1/2/4/8 B200").
+    robots_total = per_config * world if args.scaling == "weak" else per_config
     lo, hi = local_robot_range(robots_total, rank, world)
     stream = torch.cuda.Stream(device)
     peaks = {}
@@ -334,7 +338,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         (6650.0, "fallback (B200_PROFILING.md)")
 
     with torch.cuda.stream(stream):
-        arm = GpuArm(args.workload, lo, hi, device, stream, world)
+        arm = GpuArm(args.workload, lo, hi, device, stream, world, robots_total)
         # algorithmic bytes per cycle (also warms every cycle once)
         alg = [arm.algorithmic_bytes(c) for c in range(N_CYCLES)]
         for w in range(args.warmup):
@@ -396,7 +400,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32 cells / f64 geometry", "data": "synthetic",
         "config": workload_config(args.workload, world, robots_total),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -466,6 +470,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--robots", type=int, default=0, help="override the config's robot count")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: robots-per-GPU fixed (N x config robots in total); strong: config robots split over N")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip other_workloads")
     args = ap.parse_args()

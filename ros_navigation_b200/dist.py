@@ -1,0 +1,59 @@
+"""Multi-GPU plumbing for the batched mode: robots are independent, so they are block-partitioned over the ranks
+(one process per GPU) with NO collective on the data path; once per cycle the 16-byte steering commands
+(b200nav_command: speed, turnrate, picked angle, flags) of all robots are all-gathered so that every rank sees the
+whole fleet (north_star: "a single NCCL-over-NVLink allgather of per-robot steering commands and statistics per
+cycle, and only in batched mode").  The reference has no counterpart (one robot, one process; SURVEY section 2 rows
+18-19).  torch.distributed is only plumbing here: NCCL on GPUs, gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+COMMAND_BYTES = 16
+
+
+def partition(total, rank, world):
+    """Contiguous block of robots owned by `rank`: [lo, hi).  The first total % world ranks get one more."""
+    per, rem = divmod(total, world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def owner_of(robot, total, world):
+    """Rank that owns `robot` under partition()."""
+    per, rem = divmod(total, world)
+    edge = rem * (per + 1)
+    return robot // (per + 1) if robot < edge else rem + (robot - edge) // max(per, 1)
+
+
+class CommandExchange:
+    """Per-cycle all-gather of the local robots' command records into a [total, 16] uint8 table."""
+
+    def __init__(self, total, device, group=None):
+        self.total = total
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lo, self.hi = partition(total, self.rank, self.world)
+        self.n_local = self.hi - self.lo
+        self.max_local = -(-total // self.world)
+        self.even = total % self.world == 0
+        self.local = torch.zeros(self.n_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
+        self.table = torch.zeros(total, COMMAND_BYTES, dtype=torch.uint8, device=device)
+        if not self.even:  # padded staging so that every rank contributes the same number of bytes
+            self._send = torch.zeros(self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
+            self._recv = torch.zeros(self.world * self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
+
+    def gather(self):
+        """All ranks call this once per cycle after their VFH+ kernel wrote `self.local`. Returns `self.table`."""
+        if self.world == 1:
+            self.table.copy_(self.local)
+            return self.table
+        if self.even:
+            dist.all_gather_into_tensor(self.table.view(-1), self.local.view(-1), group=self.group)
+            return self.table
+        self._send[:self.n_local].copy_(self.local)
+        dist.all_gather_into_tensor(self._recv.view(-1), self._send.view(-1), group=self.group)
+        for r in range(self.world):
+            lo, hi = partition(self.total, r, self.world)
+            self.table[lo:hi].copy_(self._recv[r * self.max_local:r * self.max_local + (hi - lo)])
+        return self.table
