@@ -48,7 +48,7 @@ def local_robot_range(total, rank, world):
 class Cycles:
     """Pre-generated scan cycles for the robots [lo, hi) of a config."""
 
-    def __init__(self, cfg_name, lo, hi, device, n_cycles=N_CYCLES):
+    def __init__(self, cfg_name, lo, hi, device, n_cycles=N_CYCLES, want_samples=False):
         import torch
         from ros_navigation_b200 import synth
         self.cfg = cfg = synth.CONFIGS[cfg_name]
@@ -59,12 +59,19 @@ class Cycles:
         dt = 1.0 / cfg["rate"]
         self.dt = dt
         self.samples, self.offsets, self.inputs, self.totals = [], [], [], []
+        self.origins, self.xy, self.clear = [], [], []
         for c in range(n_cycles):
             t = c * dt * 5  # spread the replayed poses a little so cycles are distinct
             x, y, yaw = self.worlds.pose(t)
             r, ang = self.worlds.cast(x, y, yaw, cfg["beams"], cfg["fov"], cfg["range_max"])
-            s8, off = synth.samples_from_scan(x, y, yaw, r, ang, cfg["range_max"])
-            self.samples.append(s8.contiguous())
+            if want_samples:  # 40-byte RangeSamples (CPU arm)
+                s8, off = synth.samples_from_scan(x, y, yaw, r, ang, cfg["range_max"])
+                self.samples.append(s8.contiguous())
+            else:             # compact cloud form (GPU arm): origin per robot + float32 end points
+                org, xy, clr, off = synth.cloud_from_scan(x, y, yaw, r, ang, cfg["range_max"])
+                self.origins.append(org)
+                self.xy.append(xy)
+                self.clear.append(clr)
             self.offsets.append(off.contiguous())
             self.totals.append(int(off[-1]))
             self.inputs.append(synth.vfh_inputs(self.worlds, t, dt, 150).contiguous())
@@ -78,7 +85,7 @@ class Cycles:
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -88,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -104,7 +111,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, load_sm = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
@@ -113,15 +120,18 @@ class ClockSampler:
             try:
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
+                if len(parts) > 9 and float(parts[9]) > 0:
+                    load_sm.append(float(parts[1]))
             except ValueError:
                 continue
             for nm, val in zip(names, parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         if sm:
-            sm_sorted = sorted(sm)
-            out.update(sm_mhz=sm_sorted[len(sm_sorted) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons),
-                       samples=len(sm))
+            use = sorted(load_sm) if load_sm else sorted(sm)
+            out.update(sm_mhz=use[len(use) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       samples_under_load=len(load_sm),
+                       window="warm-up + timed steps + end-to-end steps (GPU busy throughout)")
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -144,7 +154,7 @@ class CpuArm:
         self.O, self.np = O, np
         self.cores = max(1, os.cpu_count() or 1)
         self.n = n_robots
-        cyc = Cycles(cfg_name, 0, n_robots, torch.device("cpu"), n_cycles=n_cycles)
+        cyc = Cycles(cfg_name, 0, n_robots, torch.device("cpu"), n_cycles=n_cycles, want_samples=True)
         self.cfg = cfg = cyc.cfg
         self.geom = O.make_geom(cfg["extent"], cfg["extent"], cfg["res"])
         self.layers = [O.new_layer(self.geom) for _ in range(n_robots)]
@@ -254,7 +264,9 @@ class GpuArm:
         self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
         self.flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=device)
         # pinned host copies for the end-to-end path
-        self.h_samples = [s.cpu().pin_memory() for s in self.cyc.samples]
+        self.h_origins = [o.cpu().pin_memory() for o in self.cyc.origins]
+        self.h_xy = [o.cpu().pin_memory() for o in self.cyc.xy]
+        self.h_clear = [o.cpu().pin_memory() for o in self.cyc.clear]
         self.h_offsets = [o.cpu().pin_memory() for o in self.cyc.offsets]
         self.h_inputs = [i.cpu().pin_memory() for i in self.cyc.inputs]
         self.d_inputs_e2e = torch.zeros_like(self.cyc.inputs[0])
@@ -266,16 +278,22 @@ class GpuArm:
 
     def step_dev(self, i):
         c = i % N_CYCLES
-        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c], self.cfg["beams"])
+        self.grid.himm_update_cloud_batched_dev("laser", self.cyc.origins[c], self.cyc.xy[c], self.cyc.clear[c],
+                                                self.cyc.offsets[c], self.cyc.totals[c], self.cfg["beams"])
         self.vfh.update_batched_dev(self.grid, "master", self.cyc.inputs[c], self.cmd)
         self.all_gather()
+
+    def step_himm_only(self, c):
+        self.grid.himm_update_cloud_batched_dev("laser", self.cyc.origins[c], self.cyc.xy[c], self.cyc.clear[c],
+                                                self.cyc.offsets[c], self.cyc.totals[c], self.cfg["beams"])
 
     def step_e2e(self, i):
         """Host buffers in, host result out: H2D of samples/offsets/VFH inputs and D2H of the commands inside."""
         c = i % N_CYCLES
         from ros_navigation_b200.capi import check, lib
-        check(lib().b200nav_himm_update_batched(self.grid.h, b"laser", self.h_samples[c].data_ptr(),
-                                                self.h_offsets[c].data_ptr(), None), self.ctx.h)
+        check(lib().b200nav_himm_update_cloud_batched(self.grid.h, b"laser", self.h_origins[c].data_ptr(),
+                                                      self.h_xy[c].data_ptr(), self.h_clear[c].data_ptr(),
+                                                      self.h_offsets[c].data_ptr(), None), self.ctx.h)
         self.d_inputs_e2e.copy_(self.h_inputs[c], non_blocking=True)
         self.vfh.update_batched_dev(self.grid, "master", self.d_inputs_e2e, self.cmd)
         self.all_gather()
@@ -284,12 +302,13 @@ class GpuArm:
         self.torch.cuda.current_stream().synchronize()
 
     def e2e_bytes(self, c):
-        h2d = self.h_samples[c].numel() + self.h_offsets[c].numel() * 4 + self.h_inputs[c].numel()
+        h2d = (self.h_origins[c].numel() * 8 + self.h_xy[c].numel() * 4 + self.h_clear[c].numel() +
+               self.h_offsets[c].numel() * 4 + self.h_inputs[c].numel())
         return h2d, self.h_cmd.numel()
 
     def algorithmic_bytes(self, c):
         """8 B per cell visit + 8 B per mark + 36 B per beam, for cycle c (this rank)."""
-        self.grid.himm_update_batched_dev("laser", self.cyc.samples[c], self.cyc.offsets[c], self.cyc.totals[c], self.cfg["beams"])
+        self.step_himm_only(c)
         visits, marks, beams = self.grid.himm_last_stats()
         return 8 * visits + 8 * marks + 36 * beams, visits, marks, beams
 
@@ -341,15 +360,16 @@ def run_gpu_arm(args, rank, world, local_rank):
         arm = GpuArm(args.workload, lo, hi, device, stream, world, robots_total)
         # algorithmic bytes per cycle (also warms every cycle once)
         alg = [arm.algorithmic_bytes(c) for c in range(N_CYCLES)]
-        for w in range(args.warmup):
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+            time.sleep(0.3)  # let nvidia-smi come up; sampling then covers warm-up, timed and end-to-end steps
+        for w in range(max(args.warmup, 50)):
             arm.step_dev(w)
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
         arm.ctx.profile_enable(True)
         launches0 = arm.ctx.launches
         t_wall0 = time.perf_counter()
@@ -421,7 +441,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         try:
             cpu = CpuArm(args.workload, cpu_sample_size(args.workload))
             t_cal = cpu.run_cycle(0)
-            n_cyc = int(max(2, min(40, 12.0 / max(t_cal, 1e-3))))
+            n_cyc = int(max(2, min(2000, 12.0 / max(t_cal, 1e-3))))
             secs = sum(cpu.run_cycle(1 + k) for k in range(n_cyc))
             line["cpu_baseline"] = {"value": cpu.n * n_cyc / secs, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
                                     "sample": "%d robots x %d cycles of workload %s (%.1f s)" % (

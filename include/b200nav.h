@@ -132,6 +132,18 @@ int b200nav_himm_update_batched(b200nav_grid* grid, const char* layer, const b20
 int b200nav_himm_update_batched_dev(b200nav_grid* grid, const char* layer, const b200nav_sample* dev_samples,
                                     const int32_t* dev_offsets, int total, int max_samples_per_robot);
 
+/* Compact "cloud" form of the same update: what LaserMapUpdater::bufferIncomingMsg actually holds per message
+ * (laser_map_updater.cpp:46-70) - ONE start point per robot (the laser origin, 2 doubles) and per cloud point the
+ * float32 x / y of the PointCloud2 plus the ifClearEnd flag - instead of 40-byte RangeSamples (5x less host->device
+ * traffic).  Equivalent to the sample form with sx,sy = origin and ex,ey = (double)x,(double)y, bit for bit.
+ *   origins: n_robots*2 doubles; xy: total*2 floats; clear_end: total bytes or NULL (all 0); offsets: n_robots+1. */
+int b200nav_himm_update_cloud_batched(b200nav_grid* grid, const char* layer, const double* host_origins,
+                                      const float* host_xy, const uint8_t* host_clear_end,
+                                      const int32_t* host_offsets, double* bbox);
+int b200nav_himm_update_cloud_batched_dev(b200nav_grid* grid, const char* layer, const double* dev_origins,
+                                          const float* dev_xy, const uint8_t* dev_clear_end,
+                                          const int32_t* dev_offsets, int total, int max_samples_per_robot);
+
 /* Work statistics of the LAST himm update of this grid (all robots of that call): out[0] = cell visits
  * (sum over beams of the Bresenham cell count), out[1] = marks, out[2] = beams.  Used for the algorithmic-byte
  * accounting of the roofline (8 B per visit + 8 B per mark + 36 B per beam). */

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "b200nav_ctx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_ctx_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b200nav_himm_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200nav_himm_update_cloud_batched": (C.c_int, [C.c_void_p, C.c_char_p] + [C.c_void_p] * 5),
+    "b200nav_himm_update_cloud_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p] + [C.c_void_p] * 4 + [C.c_int, C.c_int]),
     "b200nav_grid_create": (C.c_int, [C.c_void_p] + [C.c_double] * 5 + [C.c_int, C.POINTER(C.c_void_p)]),
     "b200nav_grid_destroy": (C.c_int, [C.c_void_p]),
     "b200nav_grid_size": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 3),

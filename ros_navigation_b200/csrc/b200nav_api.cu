@@ -109,7 +109,7 @@ struct b200nav_grid {
   std::vector<RobotGeom> geom_host;
   RobotGeom* geom_dev = nullptr;
   std::map<std::string, Layer> layers;
-  DevBuf samples, segs, offsets, occ, stats, beam_masks, col_masks, errflag;
+  DevBuf samples, segs, offsets, occ, stats, beam_masks, col_masks, errflag, origins, clearbuf;
   size_t masks_zeroed_bytes = 0, colmasks_zeroed_bytes = 0;
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
@@ -236,8 +236,14 @@ int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words) {
   return B200NAV_OK;
 }
 
+struct CloudIn {
+  const double* origins = nullptr;
+  const float* xy = nullptr;
+  const uint8_t* clear_end = nullptr;
+};
+
 int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
-                int robot0, int n_active, int single_n, int total, int max_per_robot) {
+                int robot0, int n_active, int single_n, int total, int max_per_robot, CloudIn cloud = CloudIn()) {
   b200nav_ctx* ctx = g->ctx;
   if (total <= 0) return B200NAV_OK;
   CUDA_TRY(ctx, g->segs.reserve(sizeof(BeamSeg) * (size_t)total));
@@ -246,6 +252,9 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   a.geom = g->geom_dev;
   a.layer = layer;
   a.samples = dev_samples;
+  a.origins = cloud.origins;
+  a.xy = reinterpret_cast<const float2*>(cloud.xy);
+  a.clear_end = cloud.clear_end;
   a.offsets = dev_offsets;
   a.segs = static_cast<BeamSeg*>(g->segs.p);
   a.robot0 = robot0;
@@ -566,6 +575,8 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   g->beam_masks.release();
   g->col_masks.release();
   g->errflag.release();
+  g->origins.release();
+  g->clearbuf.release();
   delete g;
   return B200NAV_OK;
 }
@@ -826,6 +837,70 @@ int b200nav_himm_update_batched_dev(b200nav_grid* g, const char* layer, const b2
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
   return himm_launch(g, l->dev, dev_samples, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot);
+}
+
+int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const double* host_origins,
+                                      const float* host_xy, const uint8_t* host_clear_end,
+                                      const int32_t* host_offsets, double* bbox) {
+  if (!g || !host_offsets || !host_origins) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  b200nav_ctx* ctx = g->ctx;
+  const int nr = g->n_robots;
+  if (host_offsets[0] != 0) return set_err(ctx, B200NAV_EINVAL, "offsets[0] must be 0");
+  int max_per = 0;
+  for (int r = 0; r < nr; r++) {
+    if (host_offsets[r + 1] < host_offsets[r]) return set_err(ctx, B200NAV_EINVAL, "offsets must be non-decreasing");
+    max_per = std::max(max_per, host_offsets[r + 1] - host_offsets[r]);
+  }
+  const int total = host_offsets[nr];
+  if (total == 0) return B200NAV_OK;
+  if (!host_xy) return B200NAV_EINVAL;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, g->samples.reserve(sizeof(float) * 2 * (size_t)total));
+  CUDA_TRY(ctx, g->offsets.reserve(sizeof(int32_t) * (size_t)(nr + 1)));
+  CUDA_TRY(ctx, g->origins.reserve(sizeof(double) * 2 * (size_t)nr));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_xy, sizeof(float) * 2 * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->offsets.p, host_offsets, sizeof(int32_t) * (size_t)(nr + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->origins.p, host_origins, sizeof(double) * 2 * (size_t)nr, cudaMemcpyHostToDevice, ctx->stream));
+  CloudIn c;
+  c.origins = static_cast<const double*>(g->origins.p);
+  c.xy = static_cast<const float*>(g->samples.p);
+  if (host_clear_end) {
+    CUDA_TRY(ctx, g->clearbuf.reserve((size_t)total));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g->clearbuf.p, host_clear_end, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    c.clear_end = static_cast<const uint8_t*>(g->clearbuf.p);
+  }
+  int rc = himm_launch(g, l->dev, nullptr, static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per, c);
+  if (rc) return rc;
+  if (bbox)
+    for (int r = 0; r < nr; r++) {
+      double* bb = bbox + 4 * r;
+      for (int i = host_offsets[r]; i < host_offsets[r + 1]; i++) { /* MapUpdater::touch on start and end */
+        const double sx = host_origins[2 * r], sy = host_origins[2 * r + 1];
+        const double ex = (double)host_xy[2 * i], ey = (double)host_xy[2 * i + 1];
+        bb[0] = std::min(std::min(bb[0], sx), ex);
+        bb[1] = std::min(std::min(bb[1], sy), ey);
+        bb[2] = std::max(std::max(bb[2], sx), ex);
+        bb[3] = std::max(std::max(bb[3], sy), ey);
+      }
+    }
+  return sync_stream(ctx);
+}
+
+int b200nav_himm_update_cloud_batched_dev(b200nav_grid* g, const char* layer, const double* dev_origins,
+                                          const float* dev_xy, const uint8_t* dev_clear_end,
+                                          const int32_t* dev_offsets, int total, int max_samples_per_robot) {
+  if (!g || !dev_offsets || !dev_origins || total < 0 || (total > 0 && !dev_xy) || max_samples_per_robot < 0)
+    return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
+  CloudIn c;
+  c.origins = dev_origins;
+  c.xy = dev_xy;
+  c.clear_end = dev_clear_end;
+  return himm_launch(g, l->dev, nullptr, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot, c);
 }
 
 int b200nav_himm_last_stats(b200nav_grid* g, int64_t* out3) {

@@ -37,7 +37,10 @@ struct HimmArgs {
   GridDims dims;
   const RobotGeom* geom;          /* [n_robots]                                   */
   float* layer;                   /* [n_robots][cols][rows]                       */
-  const b200nav_sample* samples;  /* device                                       */
+  const b200nav_sample* samples;  /* device; NULL when the cloud form below is used */
+  const double* origins;          /* cloud form: [n_active][2] laser origin per robot  */
+  const float2* xy;               /* cloud form: [total] float32 end points            */
+  const uint8_t* clear_end;       /* cloud form: [total] ifClearEnd flags or NULL      */
   const int32_t* offsets;         /* device [n_robots+1], or NULL in single mode  */
   BeamSeg* segs;                  /* device scratch [total]                       */
   /* binning scratch, all-zero between updates (the tile kernel clears what it consumes):
@@ -99,8 +102,24 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
     beg = __ldg(&a.offsets[lo]);
   }
   const RobotGeom g = a.geom[a.robot0 + rel];
-  const b200nav_sample s = a.samples[i];
-  const BeamSeg b = make_beam(a.dims, g, s.sx, s.sy, s.ex, s.ey, s.clear_end);
+  double sx, sy, ex, ey;
+  int clear_end;
+  if (a.samples) {
+    const b200nav_sample s = a.samples[i];
+    sx = s.sx;
+    sy = s.sy;
+    ex = s.ex;
+    ey = s.ey;
+    clear_end = s.clear_end;
+  } else { /* cloud form: Position(*itX, *itY) widens the float32 cloud point (laser_map_updater.cpp:60) */
+    const float2 p = a.xy[i];
+    sx = a.origins[2 * rel];
+    sy = a.origins[2 * rel + 1];
+    ex = (double)p.x;
+    ey = (double)p.y;
+    clear_end = a.clear_end ? a.clear_end[i] : 0;
+  }
+  const BeamSeg b = make_beam(a.dims, g, sx, sy, ex, ey, clear_end);
   a.segs[i] = b;
 
   const int k = i - beg; /* index of the beam within its robot */

@@ -95,6 +95,22 @@ class DeviceGridMap:
         check(lib().b200nav_himm_update_batched_dev(self.h, layer.encode(), ptr(dev_samples), ptr(dev_offsets),
                                                     int(total), int(max_per_robot)), self.ctx.h)
 
+    def himm_update_cloud_batched(self, layer, origins, xy, clear_end, offsets, bbox=None):
+        """Compact form: origins [n_robots,2] f64, xy [total,2] f32, clear_end [total] u8 or None, offsets."""
+        origins = np.ascontiguousarray(origins, dtype=np.float64)
+        xy = np.ascontiguousarray(xy, dtype=np.float32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        ce = None if clear_end is None else np.ascontiguousarray(clear_end, dtype=np.uint8)
+        check(lib().b200nav_himm_update_cloud_batched(self.h, layer.encode(), origins.ctypes.data, xy.ctypes.data,
+                                                      None if ce is None else ce.ctypes.data, offsets.ctypes.data,
+                                                      ptr(bbox)), self.ctx.h)
+
+    def himm_update_cloud_batched_dev(self, layer, dev_origins, dev_xy, dev_clear_end, dev_offsets, total,
+                                      max_per_robot):
+        check(lib().b200nav_himm_update_cloud_batched_dev(self.h, layer.encode(), ptr(dev_origins), ptr(dev_xy),
+                                                          ptr(dev_clear_end), ptr(dev_offsets), int(total),
+                                                          int(max_per_robot)), self.ctx.h)
+
     def himm_last_stats(self):
         """(cell visits, marks, beams) of the last update (roofline accounting)."""
         out = np.zeros(3, np.int64)

@@ -133,6 +133,25 @@ def samples_from_scan(x, y, yaw, ranges, ang, range_max, keep_max=False):
     return buf.view(torch.uint8).reshape(total, SAMPLE_BYTES), offsets
 
 
+def cloud_from_scan(x, y, yaw, ranges, ang, range_max, keep_max=False):
+    """Same projection as samples_from_scan in the compact cloud form of b200nav_himm_update_cloud_batched:
+    (origins f64 [n,2], xy f32 [total,2], clear_end u8 [total], offsets i32 [n+1])."""
+    n, nb = ranges.shape
+    dev = ranges.device
+    hit = ranges < range_max
+    r = torch.clamp(ranges, max=range_max)
+    th = yaw[:, None] + ang[None, :]
+    ex = (x[:, None] + r * torch.cos(th)).float()
+    ey = (y[:, None] + r * torch.sin(th)).float()
+    keep = torch.ones_like(hit) if keep_max else hit
+    offsets = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    offsets[1:] = torch.cumsum(keep.sum(dim=1), 0).int()
+    xy = torch.stack([ex[keep], ey[keep]], dim=1).contiguous()
+    clear = (~hit[keep]).to(torch.uint8).contiguous()
+    origins = torch.stack([x, y], dim=1).contiguous()
+    return origins, xy, clear, offsets
+
+
 def samples_to_numpy(samples_u8):
     from .capi import SAMPLE_DTYPE
     a = samples_u8.detach().cpu().contiguous().numpy()

@@ -150,6 +150,33 @@ def test_batched_ragged_robots(ctx):
     dg.close()
 
 
+def test_cloud_form_matches_sample_form(ctx):
+    """b200nav_himm_update_cloud_batched (origin per robot + float32 points) == the RangeSample form, bit for bit."""
+    rng = np.random.default_rng(6)
+    n_robots = 5
+    g, dg = make_pair(ctx, 12.8, 12.8, 0.05, n_robots=n_robots)
+    layers = [O.new_layer(g) for _ in range(n_robots)]
+    for cycle in range(3):
+        counts = [(0, 1080, 7, 333, 2100)[(r + cycle) % 5] for r in range(n_robots)]
+        offsets = np.zeros(n_robots + 1, np.int32)
+        offsets[1:] = np.cumsum(counts)
+        origins = rng.uniform(-3, 3, (n_robots, 2))
+        xy = rng.uniform(-8, 8, (offsets[-1], 2)).astype(np.float32)
+        clear = (rng.random(offsets[-1]) < 0.1).astype(np.uint8)
+        bb_d = np.zeros((n_robots, 4))
+        dg.himm_update_cloud_batched("laser", origins, xy, clear if cycle != 1 else None, offsets, bbox=bb_d)
+        for r in range(n_robots):
+            sl = slice(offsets[r], offsets[r + 1])
+            n = counts[r]
+            s = O.make_samples(np.full(n, origins[r, 0]), np.full(n, origins[r, 1]), xy[sl, 0].astype(np.float64),
+                               xy[sl, 1].astype(np.float64), clear[sl] if cycle != 1 else np.zeros(n, np.int32))
+            bb_o = np.zeros(4)
+            O.himm_update(g, layers[r], s, bb_o)
+            assert_layers_equal(dg.download("laser", robot=r), layers[r], "cycle %d robot %d" % (cycle, r))
+            assert np.array_equal(bb_o, bb_d[r])
+    dg.close()
+
+
 def test_c2_sized_grid_scan_sequence(ctx):
     """BASELINE config 2 geometry: 2048 x 2048 @ 5 cm, 1080-beam / 270 deg scans up to 30 m."""
     import torch
