@@ -109,7 +109,7 @@ struct b200nav_grid {
   std::vector<RobotGeom> geom_host;
   RobotGeom* geom_dev = nullptr;
   std::map<std::string, Layer> layers;
-  DevBuf samples, segs, offsets, occ, stats, beam_masks, col_masks, errflag, origins, clearbuf;
+  DevBuf samples, segs, offsets, occ, stats, beam_masks, col_masks, errflag, origins, clearbuf, touched, worklist, counters;
   size_t masks_zeroed_bytes = 0, colmasks_zeroed_bytes = 0;
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
@@ -216,7 +216,7 @@ constexpr int kSub = HIMM_TILE, kListCap = HIMM_CHUNK;
 using TileCfg = HimmTileCfg<kSub, kListCap>;
 
 /* Binning scratch: grow-only, kept all-zero between updates (the tile kernel clears what it consumes). */
-int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words) {
+int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words, size_t n_robot_tiles) {
   b200nav_ctx* ctx = g->ctx;
   const size_t mb = n_tiles_total * (size_t)mask_words * sizeof(uint32_t), cb = n_tiles_total * sizeof(unsigned long long);
   if (mb > g->beam_masks.cap) {
@@ -232,6 +232,14 @@ int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words) {
   if (!g->errflag.p) {
     CUDA_TRY(ctx, g->errflag.reserve(sizeof(int)));
     CUDA_TRY(ctx, cudaMemsetAsync(g->errflag.p, 0, sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, g->counters.reserve(4 * sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(g->counters.p, 0, g->counters.cap, ctx->stream));
+  }
+  if (n_robot_tiles * sizeof(uint32_t) > g->touched.cap) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, g->touched.reserve(n_robot_tiles * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMemsetAsync(g->touched.p, 0, g->touched.cap, ctx->stream));
+    CUDA_TRY(ctx, g->worklist.reserve(n_robot_tiles * sizeof(int)));
   }
   return B200NAV_OK;
 }
@@ -267,11 +275,15 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   a.mask_words = a.chunk_beams / 32;
   a.n_chunks = std::max(1, (max_per_robot + a.chunk_beams - 1) / a.chunk_beams);
   const size_t n_tiles_total = (size_t)n_active * a.n_chunks * a.tiles_r * a.tiles_c;
-  int rc = himm_reserve_masks(g, n_tiles_total, a.mask_words);
+  const size_t n_robot_tiles = (size_t)n_active * a.tiles_r * a.tiles_c;
+  int rc = himm_reserve_masks(g, n_tiles_total, a.mask_words, n_robot_tiles);
   if (rc) return rc;
   a.beam_masks = static_cast<uint32_t*>(g->beam_masks.p);
   a.col_masks = static_cast<unsigned long long*>(g->col_masks.p);
   a.error_flag = static_cast<int*>(g->errflag.p);
+  a.touched = static_cast<uint32_t*>(g->touched.p);
+  a.worklist = static_cast<int*>(g->worklist.p);
+  a.counters = static_cast<int*>(g->counters.p);
   g->last_total = total;
   {
     ProfScope ps(ctx, PROF_HIMM_PREP);
@@ -280,7 +292,8 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   rc = check_launch(ctx, "himm_prep_kernel");
   if (rc) return rc;
   auto kern = himm_tile_kernel<kSub, kListCap>;
-  dim3 grid((unsigned)(a.tiles_r * a.tiles_c), (unsigned)n_active);
+  /* persistent: as many one-warp CTAs as can be resident (32 per SM), never more than there are tiles */
+  dim3 grid((unsigned)std::min<size_t>(n_robot_tiles, (size_t)ctx->sm_count * 32));
   {
     ProfScope ps(ctx, PROF_HIMM_TILE);
     const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
@@ -577,6 +590,9 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   g->errflag.release();
   g->origins.release();
   g->clearbuf.release();
+  g->touched.release();
+  g->worklist.release();
+  g->counters.release();
   delete g;
   return B200NAV_OK;
 }

@@ -49,6 +49,13 @@ struct HimmArgs {
   uint32_t* beam_masks;
   unsigned long long* col_masks;
   int* error_flag;                /* set when a robot has more samples than n_chunks * HIMM_CHUNK              */
+  /* work list of touched (robot, tile) pairs, filled by the prep kernel, consumed by the persistent tile kernel:
+   *   touched[robot*n_tiles + tile]  0/1 first-touch flag (cleared by the consumer)
+   *   worklist[]                     keys robot*n_tiles + tile, in first-touch order
+   *   counters[0..2]                 entries appended / next entry to hand out / warps that finished          */
+  uint32_t* touched;
+  int* worklist;
+  int* counters;
   int robot0;                     /* first robot handled by blockIdx.y == 0       */
   int n_active;                   /* robots handled by this launch                */
   int single_n;                   /* >= 0: single-robot mode, samples [0, n)      */
@@ -59,10 +66,13 @@ struct HimmArgs {
   int mask_words;                 /* chunk_beams / 32                              */
 };
 
-__device__ __forceinline__ void himm_bin_tile(const HimmArgs& a, size_t rc_base, int tr, int tc, int word, uint32_t bit,
+__device__ __forceinline__ void himm_bin_tile(const HimmArgs& a, int rel, size_t rc_base, int tr, int tc, int word, uint32_t bit,
                                               int col_lo, int col_hi) {
   const size_t t = rc_base + (size_t)(tc * a.tiles_r + tr);
   atomicOr(&a.beam_masks[t * a.mask_words + word], bit);
+  /* first touch of this (robot, tile) in this update: append it to the work list */
+  const int rt = rel * (a.tiles_r * a.tiles_c) + tc * a.tiles_r + tr;
+  if (a.touched[rt] == 0u && atomicExch(&a.touched[rt], 1u) == 0u) a.worklist[atomicAdd(&a.counters[0], 1)] = rt;
   const int c0 = max(col_lo - tc * HIMM_TILE, 0), c1 = min(col_hi - tc * HIMM_TILE, HIMM_TILE - 1);
   if (c0 <= c1) atomicOr(&a.col_masks[t], (~0ull >> (63 - (c1 - c0))) << c0);
 }
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
   const uint32_t bit = 1u << (k & 31);
   const size_t rc_base = ((size_t)rel * a.n_chunks + chunk) * (size_t)(a.tiles_r * a.tiles_c);
 
-  if (b.mr >= 0) himm_bin_tile(a, rc_base, b.mr / HIMM_TILE, b.mc / HIMM_TILE, word, bit, b.mc, b.mc);
+  if (b.mr >= 0) himm_bin_tile(a, rel, rc_base, b.mr / HIMM_TILE, b.mc / HIMM_TILE, word, bit, b.mc, b.mc);
   if (b.r0 < 0) return;
   const LineForm f = line_form(b);
   const unsigned den = (unsigned)max(f.den, 1);
@@ -153,9 +163,9 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
     const int ma = f.m0 + f.sm * ta, mb = f.m0 + f.sm * tb;
     for (int nt = nlo / HIMM_TILE; nt <= nhi / HIMM_TILE; nt++) {
       if (f.row_major) /* rows drive: tile (band, nt); columns = minor range inside the band */
-        himm_bin_tile(a, rc_base, band, nt, word, bit, nlo, nhi);
+        himm_bin_tile(a, rel, rc_base, band, nt, word, bit, nlo, nhi);
       else /* columns drive: tile (nt, band); columns = the band's driving range (superset for this tile) */
-        himm_bin_tile(a, rc_base, nt, band, word, bit, min(ma, mb), max(ma, mb));
+        himm_bin_tile(a, rel, rc_base, nt, band, word, bit, min(ma, mb), max(ma, mb));
     }
     if (band == band1) break;
   }
@@ -467,7 +477,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
 }
 
 template <int SUB, int LIST_CAP>
-__global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
+__global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
   using Cfg = HimmTileCfg<SUB, LIST_CAP>;
   static_assert(SUB == HIMM_TILE && LIST_CAP == HIMM_CHUNK, "tile / chunk constants");
   extern __shared__ __align__(16) unsigned char himm_smem_raw[];
@@ -479,9 +489,22 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
   asm volatile("mov.u32 %0, %0;" : "+r"(tile_saddr));
 
   const int lane = threadIdx.x;
-  const int robot = a.robot0 + blockIdx.y;
-  const int tile_r = blockIdx.x % a.tiles_r, tile_c = blockIdx.x / a.tiles_r;
   const int rows = a.dims.rows, cols = a.dims.cols;
+  const int n_tiles = a.tiles_r * a.tiles_c;
+  /* float4 path: every column segment of a tile is 16-byte aligned and a whole number of quads */
+  const bool vec_ok = (rows & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.layer) & 15) == 0);
+  const int n_work = *reinterpret_cast<volatile int*>(&a.counters[0]); /* final: the prep kernel has completed */
+
+  /* ---- persistent loop: warps pull (robot, tile) work items until the list is empty ---- */
+  for (;;) {
+  int w = 0;
+  if (lane == 0) w = atomicAdd(&a.counters[1], 1);
+  w = __shfl_sync(0xffffffffu, w, 0);
+  if (w >= n_work) break;
+  const int rt = a.worklist[w];
+  const int rel = rt / n_tiles, tile_id = rt - rel * n_tiles;
+  const int robot = a.robot0 + rel;
+  const int tile_r = tile_id % a.tiles_r, tile_c = tile_id / a.tiles_r;
 
   /* tile rectangle (inclusive, clipped to the grid) */
   const int R0 = tile_r * SUB, C0 = tile_c * SUB;
@@ -489,18 +512,17 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
 
   int beg;
   if (a.single_n >= 0) beg = 0;
-  else beg = __ldg(&a.offsets[blockIdx.y]);
+  else beg = __ldg(&a.offsets[rel]);
 
   float* gbase = a.layer + (size_t)robot * rows * cols;
   float* gtile = gbase + (size_t)C0 * rows + R0;
   unsigned long long loaded = 0ull; /* columns staged in shared memory (bit c = column C0+c) */
   bool foreign = false;             /* tile holds values outside the HIMM set -> float view on global memory */
   const bool row_lo_ok = R0 + lane <= R1, row_hi_ok = R0 + lane + 32 <= R1;
-  /* float4 path: every column segment of the tile is 16-byte aligned and a whole number of quads */
-  const bool vec_ok = (rows & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.layer) & 15) == 0);
+  if (lane == 0) a.touched[rt] = 0u;
 
   for (int chunk = 0; chunk < a.n_chunks; chunk++) {
-    const size_t t = ((size_t)blockIdx.y * a.n_chunks + chunk) * (size_t)(a.tiles_r * a.tiles_c) + blockIdx.x;
+    const size_t t = ((size_t)rel * a.n_chunks + chunk) * (size_t)n_tiles + tile_id;
     /* ---- this tile's beam set: 2048-bit mask written by the prep kernel; consume and clear it ---- */
     uint32_t* mw = a.beam_masks + t * a.mask_words;
     const uint32_t w0 = (lane < a.mask_words) ? mw[lane] : 0u, w1 = (lane + 32 < a.mask_words) ? mw[lane + 32] : 0u;
@@ -688,6 +710,18 @@ __global__ void __launch_bounds__(32) himm_tile_kernel(HimmArgs a) {
         if (row_lo_ok) dst[0] = himm_decode(c0);
         if (row_hi_ok) dst[32] = himm_decode(c1);
       }
+    }
+  }
+  __syncwarp(); /* the tile buffer is reused by the next work item */
+  } /* persistent loop */
+
+  /* the last warp to finish re-arms the counters for the next update */
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(&a.counters[2], 1) == (int)gridDim.x - 1) {
+      a.counters[0] = 0;
+      a.counters[1] = 0;
+      a.counters[2] = 0;
     }
   }
 }
