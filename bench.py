@@ -478,8 +478,15 @@ def single_robot_numbers(device, name, scans=300):
         for k in range(scans):
             arm.step_e2e(k)
         e2e_s = time.perf_counter() - t0
+    arm.ctx.profile_enable(True)
+    with torch.cuda.stream(stream):
+        for k in range(50):
+            arm.step_dev(k)
+    kms = {n: (lambda t: t[0] / max(t[1], 1))(arm.ctx.profile_read(n)) for n in ("himm_prep", "himm_tile", "vfh_update")}
+    arm.ctx.profile_enable(False)
     return {"workload": workload_config(name, 1, 1)["workload"], "value": scans / (dev_ms / 1000.0),
-            "e2e": scans / e2e_s, "unit": UNIT, "ms_per_scan": dev_ms / scans, "l2": "grid (16 MiB) L2-resident"}
+            "e2e": scans / e2e_s, "unit": UNIT, "ms_per_scan": dev_ms / scans, "kernel_ms": kms,
+            "l2": "grid (16 MiB) L2-resident"}
 
 
 def main():

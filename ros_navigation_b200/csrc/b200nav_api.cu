@@ -279,7 +279,6 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   int rc = himm_reserve_masks(g, n_tiles_total, a.mask_words, n_robot_tiles);
   if (rc) return rc;
   a.beam_masks = static_cast<uint32_t*>(g->beam_masks.p);
-  a.col_masks = static_cast<unsigned long long*>(g->col_masks.p);
   a.error_flag = static_cast<int*>(g->errflag.p);
   a.touched = static_cast<uint32_t*>(g->touched.p);
   a.worklist = static_cast<int*>(g->worklist.p);
@@ -557,6 +556,7 @@ int b200nav_grid_create(b200nav_ctx* ctx, double len_x, double len_y, double res
   g->dims.res = res;
   g->dims.len_x = (double)g->dims.rows * res;
   g->dims.len_y = (double)g->dims.cols * res;
+  g->dims.rres = 1.0 / res;
   g->n_robots = n_robots;
   RobotGeom rg;
   rg.pos_x = pos_x;

@@ -14,6 +14,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define B200_HD __host__ __device__ __forceinline__
@@ -28,6 +29,7 @@ struct GridDims {
   int rows, cols;
   double res;
   double len_x, len_y;
+  double rres; /* RN(1/res), for f64_div_by */
 };
 
 /* Per-robot part: map centre and circular-buffer start index. */
@@ -37,6 +39,84 @@ struct RobotGeom {
 };
 
 #define B200NAV_DBL_EPSILON 2.2204460492503131e-16
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * fp64 helpers that avoid the 64-bit XU operations (MUFU.RCP64H, F2I.F64, I2F.F64, F2F.F64.F32).  On B200 those
+ * issue at ~1/64 of the warp rate (ncu: the prep kernel sat at 75 % XU-pipe utilisation with < 3 % of its
+ * instructions being such operations).  Every helper returns bit-for-bit what the plain C++ expression returns.
+ * ------------------------------------------------------------------------------------------------------------- */
+B200_HD unsigned long long f64_bits(double v) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned long long)__double_as_longlong(v);
+#else
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return b;
+#endif
+}
+B200_HD double f64_from_bits(unsigned long long b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+#endif
+}
+
+/* (double)k for any int32 k: 2^52 + 2^31 + k is exact in the low mantissa bits. */
+B200_HD double int_to_f64(int k) {
+  return f64_from_bits(0x4330000000000000ull | (unsigned long long)((unsigned)k ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+/* (int)v (C truncation toward zero) for |v| < 2^31. */
+B200_HD int f64_trunc_to_int(double v) {
+  const double t = v + 6755399441055744.0; /* 2^52 + 2^51: round to nearest integer into the low bits */
+  int n = (int)(unsigned)(f64_bits(t) & 0xffffffffull);
+  const double nd = t - 6755399441055744.0;
+  if (v >= 0.0) {
+    if (nd > v) n -= 1;
+  } else {
+    if (nd < v) n += 1;
+  }
+  return n;
+}
+
+/* (double)f for a float f. */
+B200_HD double f32_to_f64(float f) {
+#if defined(__CUDA_ARCH__)
+  const unsigned u = __float_as_uint(f);
+#else
+  unsigned u;
+  memcpy(&u, &f, 4);
+#endif
+  const unsigned e = (u >> 23) & 0xffu;
+  if (e != 0u && e != 255u) /* normal: re-bias the exponent, widen the mantissa */
+    return f64_from_bits(((unsigned long long)(u & 0x80000000u) << 32) | ((unsigned long long)(e + 896u) << 52) |
+                         ((unsigned long long)(u & 0x7fffffu) << 29));
+  return (double)f; /* zero, subnormal, inf, NaN */
+}
+
+/* a / b, correctly rounded, given y = RN(1/b) (precomputed once with a true division): Markstein iteration
+ * q1 = q0 + (a - q0*b)*y, then an exact-remainder check against the neighbouring double, so the result is the
+ * IEEE quotient whatever b is.  Valid for finite a, b with the quotient in the normal range (all uses here:
+ * |a| < 1e6 m, b = the grid resolution). */
+B200_HD double f64_div_by(double a, double b, double y) {
+  const double q0 = a * y;
+  const double r0 = fma(-q0, b, a);
+  const double q1 = fma(r0, y, q0);
+  const double r1 = fma(-q1, b, a);
+  if (r1 == 0.0) return q1;
+  /* neighbour of q1 on the side of the true quotient */
+  const bool up = (r1 > 0.0) == (b > 0.0);
+  unsigned long long qb = f64_bits(q1);
+  if (q1 == 0.0) return q1;
+  const bool away = (q1 > 0.0) == up; /* moving away from zero increments the bit pattern */
+  qb = away ? qb + 1ull : qb - 1ull;
+  const double qn = f64_from_bits(qb);
+  const double r2 = fma(-qn, b, a);
+  return (fabs(r2) < fabs(r1)) ? qn : q1;
+}
 
 /* One Bresenham line in buffer-index space + the cell to mark. 24 bytes. */
 struct BeamSeg {
@@ -58,12 +138,12 @@ B200_HD bool within_map(double px, double py, double lx, double ly, double mx, d
 
 /* position -> buffer index: -trunc(((p - L/2) - c) / res), then + startIndex mod size. */
 B200_HD bool index_from_position(double px, double py, double lx, double ly, double mx, double my, double res,
-                                 int rows, int cols, int s0, int s1, int& r, int& c) {
+                                 double rres, int rows, int cols, int s0, int s1, int& r, int& c) {
   if (!within_map(px, py, lx, ly, mx, my)) return false;
-  const double vx = ((px - 0.5 * lx) - mx) / res;
-  const double vy = ((py - 0.5 * ly) - my) / res;
-  int i0 = -static_cast<int>(vx);
-  int i1 = -static_cast<int>(vy);
+  const double vx = f64_div_by((px - 0.5 * lx) - mx, res, rres); /* == ((px - 0.5*lx) - mx) / res */
+  const double vy = f64_div_by((py - 0.5 * ly) - my, res, rres);
+  int i0 = -f64_trunc_to_int(vx);                                 /* == -static_cast<int>(vx)       */
+  int i1 = -f64_trunc_to_int(vy);
   if ((s0 | s1) != 0) {
     i0 += s0;
     i1 += s1;
@@ -76,8 +156,8 @@ B200_HD bool index_from_position(double px, double py, double lx, double ly, dou
 }
 
 B200_HD bool grid_index(const GridDims& d, const RobotGeom& g, double px, double py, int& r, int& c) {
-  return index_from_position(px, py, d.len_x, d.len_y, g.pos_x, g.pos_y, d.res, d.rows, d.cols, g.start0, g.start1,
-                             r, c);
+  return index_from_position(px, py, d.len_x, d.len_y, g.pos_x, g.pos_y, d.res, d.rres, d.rows, d.cols, g.start0,
+                             g.start1, r, c);
 }
 
 /* buffer index -> cell centre: (c + (L/2 - res/2)) + res * (-(unwrapped index)). */
@@ -90,8 +170,8 @@ B200_HD void position_from_index(int r, int c, double lx, double ly, double mx, 
     wrap_index(u0, rows);
     wrap_index(u1, cols);
   }
-  px = (mx + (0.5 * lx - 0.5 * res)) + res * static_cast<double>(-u0);
-  py = (my + (0.5 * ly - 0.5 * res)) + res * static_cast<double>(-u1);
+  px = (mx + (0.5 * lx - 0.5 * res)) + res * int_to_f64(-u0);
+  py = (my + (0.5 * ly - 0.5 * res)) + res * int_to_f64(-u1);
 }
 
 B200_HD void limit_position_to_range(double& px, double& py, double lx, double ly, double mx, double my) {
@@ -208,7 +288,7 @@ B200_HD bool submap_info(const GridDims& d, const RobotGeom& g, double cx, doubl
   cyp -= -half;
   const int sr = br - utr + 1, sc = bc - utc + 1;
   if (sr <= 0 || sc <= 0) return false;
-  const double slx = static_cast<double>(sr) * d.res, sly = static_cast<double>(sc) * d.res;
+  const double slx = int_to_f64(sr) * d.res, sly = int_to_f64(sc) * d.res;
   const double spx = cxp - 0.5 * slx, spy = cyp - 0.5 * sly;
   if (!within_map(cx, cy, slx, sly, spx, spy)) return false;
   if (utr + sr > d.rows || utc + sc > d.cols) return false;

@@ -198,7 +198,7 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
           value = lay[(size_t)b1 * ga.dims.rows + b0];
         }
         if (isnan(value) || value <= c.occupied_threshold) continue;
-        const double px = offx + res * (double)(-i0), py = offy + res * (double)(-i1);
+        const double px = offx + res * int_to_f64(-i0), py = offy + res * int_to_f64(-i1);
         const double angle = atan2(py - inp.y, px - inp.x);
         const double a = angle - inp.yaw + 3.14 / 2;
         const double twopi = 2.0 * 3.14159265358979323846;

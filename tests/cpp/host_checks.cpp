@@ -38,6 +38,51 @@ static long long g_checks = 0;
 
 static bool same_bits(double a, double b) { return std::memcmp(&a, &b, 8) == 0; }
 
+/* the XU-free fp64 helpers of geometry.h against the plain C++ expressions they stand for */
+static int check_f64_helpers(unsigned seed, long long n) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  const double res_list[] = {0.05, 0.02, 1.0, 0.1, 0.03, 0.025, 0.3, 1.0 / 3.0, 0.0499999999999, 7.0, 0.001};
+  for (double res : res_list) {
+    const double y = 1.0 / res;
+    for (long long i = 0; i < n; i++) {
+      double a;
+      switch (i % 4) {
+        case 0: a = U(rng) * 200.0; break;
+        case 1: a = res * (double)(long long)(U(rng) * 4000.0); break;             /* near exact multiples */
+        case 2: a = res * (double)(long long)(U(rng) * 4000.0) * (1.0 + U(rng) * 4e-16); break;
+        default: a = U(rng) * 1e-3; break;
+      }
+      const double want = a / res, got = f64_div_by(a, res, y);
+      g_checks++;
+      if (!same_bits(want, got)) FAIL("f64_div_by(%.17g, %.17g): %.17g vs %.17g", a, res, got, want);
+      if (std::fabs(want) < 2147483000.0) {
+        if (f64_trunc_to_int(want) != static_cast<int>(want)) FAIL("f64_trunc_to_int(%.17g)", want);
+      }
+    }
+  }
+  for (long long i = 0; i < n; i++) {
+    const int k = (int)rng();
+    g_checks++;
+    if (!same_bits(int_to_f64(k), static_cast<double>(k))) FAIL("int_to_f64(%d)", k);
+    const double v = (double)((long long)(rng() % 4000001) - 2000000) + ((i & 1) ? 0.0 : U(rng));
+    if (f64_trunc_to_int(v) != static_cast<int>(v)) FAIL("f64_trunc_to_int(%.17g)", v);
+    unsigned u = (unsigned)rng();
+    if (i % 7 == 0) u &= 0x807fffffu; /* zeros / subnormals */
+    float f;
+    std::memcpy(&f, &u, 4);
+    const double d1 = f32_to_f64(f), d2 = (double)f;
+    if (!(same_bits(d1, d2) || (std::isnan(d1) && std::isnan(d2)))) FAIL("f32_to_f64(0x%08x)", u);
+  }
+  const int ks[] = {0, 1, -1, 2147483647, -2147483647 - 1, 32767, -32768};
+  for (int k : ks)
+    if (!same_bits(int_to_f64(k), static_cast<double>(k))) FAIL("int_to_f64 edge %d", k);
+  const double vs[] = {0.0, -0.0, 0.5, -0.5, 0.9999999999999999, -0.9999999999999999, 1.0, -1.0, 2.5, -2.5, 3.5, -3.5, 1e9, -1e9};
+  for (double v : vs)
+    if (f64_trunc_to_int(v) != static_cast<int>(v)) FAIL("f64_trunc_to_int edge %.17g", v);
+  return 0;
+}
+
 static int check_geometry(unsigned seed, int iters) {
   std::mt19937_64 rng(seed);
   std::uniform_real_distribution<double> U(0.0, 1.0);
@@ -51,7 +96,7 @@ static int check_geometry(unsigned seed, int iters) {
       og.start0 = (int)(rng() % og.rows);
       og.start1 = (int)(rng() % og.cols);
     }
-    GridDims d{og.rows, og.cols, og.res, og.len_x, og.len_y};
+    GridDims d{og.rows, og.cols, og.res, og.len_x, og.len_y, 1.0 / og.res};
     RobotGeom g{og.pos_x, og.pos_y, og.start0, og.start1};
     for (int k = 0; k < 200; k++) {
       const double x = og.pos_x + (U(rng) - 0.5) * og.len_x * 1.6, y = og.pos_y + (U(rng) - 0.5) * og.len_y * 1.6;
@@ -210,6 +255,7 @@ static int check_vfh_tables(const b200nav_vfh_params& p) {
 
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 40;
+  if (check_f64_helpers(777u, 200000LL * (iters > 100 ? 10 : 1))) return 1;
   if (check_geometry(12345u, iters)) return 1;
   b200nav_vfh_params p;
   memset(&p, 0, sizeof(p));
