@@ -98,6 +98,9 @@ struct DevBuf {
 struct Layer {
   float* dev = nullptr;
   bool owned = true;
+  /* [n_robots * n_tiles] free-column summaries of the HIMM tile kernel (shared with aliases of this layer);
+   * all-zero = nothing known.  Every writer of the layer other than the tile kernel resets it. */
+  unsigned long long* free_cols = nullptr;
 };
 
 }  // namespace
@@ -195,6 +198,21 @@ Layer* find_layer(b200nav_grid* g, const char* name) {
   return it == g->layers.end() ? nullptr : &it->second;
 }
 
+size_t grid_tiles(const b200nav_grid* g) {
+  return (size_t)((g->dims.rows + HIMM_TILE - 1) / HIMM_TILE) * ((g->dims.cols + HIMM_TILE - 1) / HIMM_TILE);
+}
+
+/* Forget what is known about free columns of `l` (robot < 0: all robots) - after any write that is not HIMM. */
+int reset_free_cols(b200nav_grid* g, Layer* l, int robot) {
+  if (!l->free_cols) return B200NAV_OK;
+  const size_t nt = grid_tiles(g);
+  if (robot < 0)
+    CUDA_TRY(g->ctx, cudaMemsetAsync(l->free_cols, 0, sizeof(unsigned long long) * nt * g->n_robots, g->ctx->stream));
+  else
+    CUDA_TRY(g->ctx, cudaMemsetAsync(l->free_cols + nt * robot, 0, sizeof(unsigned long long) * nt, g->ctx->stream));
+  return B200NAV_OK;
+}
+
 int fill_nan(b200nav_grid* g, float* p, size_t n) {
   const int threads = 256;
   const size_t blocks = std::min<size_t>((n + threads - 1) / threads, (size_t)g->ctx->sm_count * 16);
@@ -232,7 +250,7 @@ int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words, si
   if (!g->errflag.p) {
     CUDA_TRY(ctx, g->errflag.reserve(sizeof(int)));
     CUDA_TRY(ctx, cudaMemsetAsync(g->errflag.p, 0, sizeof(int), ctx->stream));
-    CUDA_TRY(ctx, g->counters.reserve(4 * sizeof(int)));
+    CUDA_TRY(ctx, g->counters.reserve(8 * sizeof(int)));
     CUDA_TRY(ctx, cudaMemsetAsync(g->counters.p, 0, g->counters.cap, ctx->stream));
   }
   if (n_robot_tiles * sizeof(uint32_t) > g->touched.cap) {
@@ -250,7 +268,7 @@ struct CloudIn {
   const uint8_t* clear_end = nullptr;
 };
 
-int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
+int himm_launch(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
                 int robot0, int n_active, int single_n, int total, int max_per_robot, CloudIn cloud = CloudIn()) {
   b200nav_ctx* ctx = g->ctx;
   if (total <= 0) return B200NAV_OK;
@@ -258,7 +276,8 @@ int himm_launch(b200nav_grid* g, float* layer, const b200nav_sample* dev_samples
   HimmArgs a;
   a.dims = g->dims;
   a.geom = g->geom_dev;
-  a.layer = layer;
+  a.layer = lay->dev;
+  a.free_cols = lay->free_cols + grid_tiles(g) * (size_t)robot0;
   a.samples = dev_samples;
   a.origins = cloud.origins;
   a.xy = reinterpret_cast<const float2*>(cloud.xy);
@@ -578,7 +597,10 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
   for (auto& kv : g->layers)
-    if (kv.second.owned && kv.second.dev) cudaFree(kv.second.dev);
+    if (kv.second.owned && kv.second.dev) {
+      cudaFree(kv.second.dev);
+      cudaFree(kv.second.free_cols);
+    }
   if (g->geom_dev) cudaFree(g->geom_dev);
   g->samples.release();
   g->segs.release();
@@ -616,6 +638,9 @@ int b200nav_grid_add_layer(b200nav_grid* g, const char* name) {
     cudaFree(l.dev);
     return rc;
   }
+  const size_t fc_bytes = sizeof(unsigned long long) * grid_tiles(g) * g->n_robots;
+  CUDA_TRY(g->ctx, cudaMalloc((void**)&l.free_cols, fc_bytes));
+  CUDA_TRY(g->ctx, cudaMemsetAsync(l.free_cols, 0, fc_bytes, g->ctx->stream));
   g->layers[name] = l;
   return B200NAV_OK;
 }
@@ -628,9 +653,11 @@ int b200nav_grid_alias_layer(b200nav_grid* g, const char* alias, const char* tar
   if (a && a->owned && a->dev && a->dev != t->dev) {
     cudaStreamSynchronize(g->ctx->stream);
     cudaFree(a->dev);
+    cudaFree(a->free_cols);
   }
   Layer l;
   l.dev = t->dev;
+  l.free_cols = t->free_cols;
   l.owned = false;
   g->layers[alias] = l;
   return B200NAV_OK;
@@ -643,6 +670,9 @@ int b200nav_grid_copy_layer(b200nav_grid* g, const char* dst, const char* src) {
   if (d->dev == s->dev) return B200NAV_OK;
   CUDA_TRY(g->ctx, cudaMemcpyAsync(d->dev, s->dev, g->layer_elems() * sizeof(float), cudaMemcpyDeviceToDevice,
                                    g->ctx->stream));
+  /* the copy carries the source's free-column knowledge along */
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(d->free_cols, s->free_cols, sizeof(unsigned long long) * grid_tiles(g) * g->n_robots,
+                                   cudaMemcpyDeviceToDevice, g->ctx->stream));
   return B200NAV_OK;
 }
 
@@ -651,11 +681,15 @@ int b200nav_grid_clear(b200nav_grid* g, const char* layer) {
   if (layer) {
     Layer* l = find_layer(g, layer);
     if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer);
+    int rc = reset_free_cols(g, l, -1);
+    if (rc) return rc;
     return fill_nan(g, l->dev, g->layer_elems());
   }
   for (auto& kv : g->layers)
     if (kv.second.owned) {
-      int rc = fill_nan(g, kv.second.dev, g->layer_elems());
+      int rc = reset_free_cols(g, &kv.second, -1);
+      if (rc) return rc;
+      rc = fill_nan(g, kv.second.dev, g->layer_elems());
       if (rc) return rc;
     }
   return B200NAV_OK;
@@ -666,6 +700,8 @@ int b200nav_grid_upload(b200nav_grid* g, int robot, const char* layer, const flo
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   const size_t n = (size_t)g->dims.rows * g->dims.cols;
+  int rrc = reset_free_cols(g, l, robot);
+  if (rrc) return rrc;
   CUDA_TRY(g->ctx, cudaMemcpyAsync(l->dev + n * robot, colmajor, n * sizeof(float), cudaMemcpyHostToDevice,
                                    g->ctx->stream));
   return sync_stream(g->ctx);
@@ -723,6 +759,8 @@ int b200nav_grid_move(b200nav_grid* g, int robot, double x, double y, int* moved
     if (n <= 0) return B200NAV_OK;
     for (auto& kv : g->layers) {
       if (!kv.second.owned) continue;
+      int rrc = reset_free_cols(g, &kv.second, robot);
+      if (rrc) return rrc;
       float* base = kv.second.dev + per_robot * robot;
       const int r0 = axis == 0 ? index : 0, nr = axis == 0 ? n : g->dims.rows;
       const int c0 = axis == 1 ? index : 0, nc = axis == 1 ? n : g->dims.cols;
@@ -808,7 +846,7 @@ int b200nav_himm_update(b200nav_grid* g, int robot, const char* layer, const b20
   CUDA_TRY(ctx, g->samples.reserve(sizeof(b200nav_sample) * (size_t)n));
   CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_samples, sizeof(b200nav_sample) * (size_t)n,
                                 cudaMemcpyHostToDevice, ctx->stream));
-  int rc = himm_launch(g, l->dev, static_cast<const b200nav_sample*>(g->samples.p), nullptr, robot, 1, n, n, n);
+  int rc = himm_launch(g, l, static_cast<const b200nav_sample*>(g->samples.p), nullptr, robot, 1, n, n, n);
   if (rc) return rc;
   if (bbox) host_touch(host_samples, n, bbox); /* overlaps the kernels */
   return sync_stream(ctx);
@@ -836,7 +874,7 @@ int b200nav_himm_update_batched(b200nav_grid* g, const char* layer, const b200na
                                 cudaMemcpyHostToDevice, ctx->stream));
   int max_per = 0;
   for (int r = 0; r < nr; r++) max_per = std::max(max_per, host_offsets[r + 1] - host_offsets[r]);
-  int rc = himm_launch(g, l->dev, static_cast<const b200nav_sample*>(g->samples.p),
+  int rc = himm_launch(g, l, static_cast<const b200nav_sample*>(g->samples.p),
                        static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per);
   if (rc) return rc;
   if (bbox)
@@ -852,7 +890,7 @@ int b200nav_himm_update_batched_dev(b200nav_grid* g, const char* layer, const b2
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
-  return himm_launch(g, l->dev, dev_samples, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot);
+  return himm_launch(g, l, dev_samples, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot);
 }
 
 int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const double* host_origins,
@@ -887,7 +925,7 @@ int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const 
     CUDA_TRY(ctx, cudaMemcpyAsync(g->clearbuf.p, host_clear_end, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
     c.clear_end = static_cast<const uint8_t*>(g->clearbuf.p);
   }
-  int rc = himm_launch(g, l->dev, nullptr, static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per, c);
+  int rc = himm_launch(g, l, nullptr, static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per, c);
   if (rc) return rc;
   if (bbox)
     for (int r = 0; r < nr; r++) {
@@ -916,7 +954,7 @@ int b200nav_himm_update_cloud_batched_dev(b200nav_grid* g, const char* layer, co
   c.origins = dev_origins;
   c.xy = dev_xy;
   c.clear_end = dev_clear_end;
-  return himm_launch(g, l->dev, nullptr, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot, c);
+  return himm_launch(g, l, nullptr, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot, c);
 }
 
 int b200nav_himm_last_stats(b200nav_grid* g, int64_t* out3) {
@@ -1183,6 +1221,21 @@ int b200nav_vfh_get_tables(const b200nav_vfh* v, int table, float* dir, float* d
     memcpy(sector_masks, t.masks_xy.data() + (size_t)table * ww * t.c.nwords, ww * t.c.nwords * sizeof(uint32_t));
   if (min_turning_radius)
     memcpy(min_turning_radius, t.min_turning_radius.data(), t.min_turning_radius.size() * sizeof(int32_t));
+  return B200NAV_OK;
+}
+
+/* Statistics hook (not part of the drop-in surface): out[0] = tile work items skipped by the free-space shortcut,
+ * out[1] = processed, since the last call. */
+int b200nav_himm_debug_tile_stats(b200nav_grid* g, int64_t* out2) {
+  if (!g || !out2) return B200NAV_EINVAL;
+  out2[0] = out2[1] = 0;
+  if (!g->counters.p) return B200NAV_OK;
+  int c[8];
+  CUDA_TRY(g->ctx, cudaStreamSynchronize(g->ctx->stream));
+  CUDA_TRY(g->ctx, cudaMemcpy(c, g->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+  out2[0] = c[4];
+  out2[1] = c[5];
+  CUDA_TRY(g->ctx, cudaMemset(static_cast<int*>(g->counters.p) + 4, 0, 2 * sizeof(int)));
   return B200NAV_OK;
 }
 

@@ -55,6 +55,10 @@ struct HimmArgs {
   uint32_t* touched;
   int* worklist;
   int* counters;
+  /* free_cols[robot*n_tiles + tile]: bit c set => every cell of column c of that tile holds exactly 0 (free).
+   * Maintained by the tile kernel at write-back, reset by every other writer of the layer.  A tile whose beams
+   * only cross free columns and carry no mark cannot change (clearing 0 gives 0) and is skipped outright. */
+  unsigned long long* free_cols;
   int robot0;                     /* first robot handled by blockIdx.y == 0       */
   int n_active;                   /* robots handled by this launch                */
   int single_n;                   /* >= 0: single-robot mode, samples [0, n)      */
@@ -561,6 +565,8 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
   bool foreign = false;             /* tile holds values outside the HIMM set -> float view on global memory */
   const bool row_lo_ok = R0 + lane <= R1, row_hi_ok = R0 + lane + 32 <= R1;
   if (lane == 0) a.touched[rt] = 0u;
+  const unsigned long long free_known = a.free_cols[rt]; /* warp-uniform load */
+  bool can_skip = true;
 
   for (int chunk = 0; chunk < a.n_chunks; chunk++) {
     const size_t t = ((size_t)rel * a.n_chunks + chunk) * (size_t)n_tiles + tile_id;
@@ -595,19 +601,33 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
     /* ---- which columns of the tile may be touched?  Conservative: bounding box of each listed beam intersected
      * with the tile (a superset only costs a few extra column loads / stores of unchanged data). ---- */
     unsigned long long need = 0ull;
+    bool any_mark = false;
     for (int j = lane; j < n_list; j += 32) {
       const BeamSeg b = segs[list[j]];
       if (b.r0 >= 0 && max(b.r0, b.r1) >= R0 && min(b.r0, b.r1) <= R1) {
         const int ca = max(min(b.c0, b.c1), C0), cb = min(max(b.c0, b.c1), C1);
         if (ca <= cb) need |= (~0ull >> (63 - (cb - ca))) << (ca - C0);
       }
-      if (b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1) need |= 1ull << (b.mc - C0);
+      if (b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1) {
+        need |= 1ull << (b.mc - C0);
+        any_mark = true;
+      }
     }
+    {
+      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)need), hi = __reduce_or_sync(0xffffffffu, (unsigned)(need >> 32));
+      need = ((unsigned long long)hi << 32) | lo;
+    }
+    /* ---- free-space shortcut: only clears, only on columns known to hold nothing but 0 -> nothing can change ---- */
+    if (can_skip && !__any_sync(0xffffffffu, any_mark) && (need & ~free_known) == 0ull) {
+      if (lane == 0) atomicAdd(&a.counters[4], 1); /* statistics: tiles skipped */
+      continue;
+    }
+    if (lane == 0) atomicAdd(&a.counters[5], 1);   /* statistics: tiles processed */
+    can_skip = false; /* the tile is being modified from here on: later chunks must not trust free_known */
 
     if (!foreign) {
       /* ---- stage the newly needed columns: float -> code ---- */
-      unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)need), hi = __reduce_or_sync(0xffffffffu, (unsigned)(need >> 32));
-      unsigned long long m = (((unsigned long long)hi << 32) | lo) & ~loaded;
+      unsigned long long m = need & ~loaded;
       loaded |= m;
       unsigned bad = 0;
       if (vec_ok) {
@@ -717,9 +737,10 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
     __syncwarp(); /* the list is rewritten by the next chunk */
   }
 
-  /* ---- write back the staged (== possibly touched) columns: code -> float, coalesced 256-byte segments ---- */
-  {
-    unsigned long long m = loaded;
+  /* ---- write back the staged (== possibly touched) columns: code -> float, coalesced 256-byte segments; and
+   * refresh the free-column summary of exactly those columns ---- */
+  if (loaded || foreign) {
+    unsigned long long m = loaded, now_free = 0ull;
     if (vec_ok) {
       const int half = lane >> 4, quad = lane & 15;
       const bool quad_ok = R0 + 4 * quad <= R1;
@@ -736,10 +757,12 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
             w32 &= w32 - 1;
           }
           const int c = (half ? cb : ca);
+          bool quad_free = true; /* rows outside the grid count as free */
           if (c >= 0 && quad_ok) {
             const int cc = c + 32 * h;
             uint32_t w;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(my_saddr + cc * Cfg::kPitch) : "memory");
+            quad_free = (w == 0x01010101u);
             float4 o;
             o.x = himm_decode(w & 0xffu);
             o.y = himm_decode((w >> 8) & 0xffu);
@@ -747,6 +770,9 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
             o.w = himm_decode(w >> 24);
             *reinterpret_cast<float4*>(my_g + (unsigned)(cc * rows)) = o;
           }
+          const unsigned fb = __ballot_sync(0xffffffffu, quad_free);
+          if ((fb & 0xffffu) == 0xffffu) now_free |= 1ull << (ca + 32 * h);
+          if (cb >= 0 && (fb >> 16) == 0xffffu) now_free |= 1ull << (cb + 32 * h);
         }
       }
     } else {
@@ -757,8 +783,12 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
         const unsigned c0 = tile[c * Cfg::kPitch + lane], c1 = tile[c * Cfg::kPitch + lane + 32];
         if (row_lo_ok) dst[0] = himm_decode(c0);
         if (row_hi_ok) dst[32] = himm_decode(c1);
+        if (__all_sync(0xffffffffu, (!row_lo_ok || c0 == 1u) && (!row_hi_ok || c1 == 1u))) now_free |= 1ull << c;
       }
     }
+    /* columns not staged keep what was known about them; a tile processed in place (foreign values) knows nothing */
+    const unsigned long long upd = foreign ? 0ull : ((free_known & ~loaded) | now_free);
+    if (lane == 0 && upd != free_known) a.free_cols[rt] = upd;
   }
   __syncwarp(); /* the tile buffer is reused by the next work item */
   } /* persistent loop */

@@ -150,6 +150,52 @@ def test_batched_ragged_robots(ctx):
     dg.close()
 
 
+def test_free_tile_shortcut_sees_external_writes(ctx):
+    """The tile kernel skips tiles whose beams only clear columns known to be all 0.  Every other writer of the layer
+    (upload, clear, move, copy) must invalidate that knowledge: interleave them with clear-only scans."""
+    rng = np.random.default_rng(8)
+    g, dg = make_pair(ctx, 12.8, 12.8, 0.05, layers=("laser", "master"))
+    layer = O.new_layer(g)
+    origin = (0.3, -0.2)
+
+    def scans(n, clear_frac):
+        for _ in range(n):
+            s = lidar_samples(rng, g, origin, 720, 3.0, 5.5, clear_frac=clear_frac)
+            O.himm_update(g, layer, s)
+            dg.himm_update("laser", s)
+
+    scans(25, 0.0)                      # marks at the ends, everything in between becomes 0
+    scans(3, 1.0)                       # clear-only: large all-free regions are now known and skipped
+    assert_layers_equal(dg.download("laser"), layer, "after warm-up")
+    # (1) upload: plant obstacles and unknown cells inside the free region
+    ys, xs = np.nonzero(layer == 0.0)
+    pick = rng.choice(len(ys), 400, replace=False)
+    layer[ys[pick[:200]], xs[pick[:200]]] = 90.0
+    layer[ys[pick[200:]], xs[pick[200:]]] = np.nan
+    dg.upload("laser", layer)
+    scans(2, 1.0)
+    assert_layers_equal(dg.download("laser"), layer, "after upload")
+    # (2) copy from another layer
+    other = layer.copy()
+    other[other == 0.0] = 40.0
+    dg.upload("master", other)
+    dg.copy_layer("laser", "master")
+    layer[:] = other
+    scans(2, 1.0)
+    assert_layers_equal(dg.download("laser"), layer, "after copy_layer")
+    # (3) move: strips become NaN
+    scans(6, 1.0)
+    assert O.move(g, [layer], 1.0, -0.6) == dg.move((1.0, -0.6))
+    scans(2, 1.0)
+    assert_layers_equal(dg.download("laser"), layer, "after move")
+    # (4) clear
+    dg.clear("laser")
+    layer[:] = np.nan
+    scans(2, 0.5)
+    assert_layers_equal(dg.download("laser"), layer, "after clear")
+    dg.close()
+
+
 def test_cloud_form_matches_sample_form(ctx):
     """b200nav_himm_update_cloud_batched (origin per robot + float32 points) == the RangeSample form, bit for bit."""
     rng = np.random.default_rng(6)
