@@ -302,6 +302,7 @@ int himm_launch(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, 
   a.touched = static_cast<uint32_t*>(g->touched.p);
   a.worklist = static_cast<int*>(g->worklist.p);
   a.counters = static_cast<int*>(g->counters.p);
+  a.worklist_cap = (int)n_robot_tiles;
   g->last_total = total;
   {
     ProfScope ps(ctx, PROF_HIMM_PREP);

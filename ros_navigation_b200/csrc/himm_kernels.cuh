@@ -51,9 +51,11 @@ struct HimmArgs {
   /* work list of touched (robot, tile) pairs, filled by the prep kernel, consumed by the persistent tile kernel:
    *   touched[robot*n_tiles + tile]  0/1 first-touch flag (cleared by the consumer)
    *   worklist[]                     keys robot*n_tiles + tile, in first-touch order
-   *   counters[0..2]                 entries appended / next entry to hand out / warps that finished          */
+   *   counters[0..3]                 heavy entries (front) / next entry to hand out / warps finished / light
+   *                                  entries (appended from the back)                                           */
   uint32_t* touched;
   int* worklist;
+  int worklist_cap;               /* entries in worklist[] (n_active * n_tiles)                              */
   int* counters;
   /* free_cols[robot*n_tiles + tile]: bit c set => every cell of column c of that tile holds exactly 0 (free).
    * Maintained by the tile kernel at write-back, reset by every other writer of the layer.  A tile whose beams
@@ -211,7 +213,13 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
       atomicOr(&a.beam_masks[widx], bits);
       /* first touch of this (robot, tile) in this update: append it to the work list */
       const int rt = rel * n_tiles + tile_id;
-      if (a.touched[rt] == 0u && atomicExch(&a.touched[rt], 1u) == 0u) a.worklist[atomicAdd(&a.counters[0], 1)] = rt;
+      if (a.touched[rt] == 0u && atomicExch(&a.touched[rt], 1u) == 0u) {
+        /* The tile that holds the beams' own start cell sees every beam of the scan: such heavy items are queued
+         * from the front of the list, all others from the back, so the long items start first (no long tail). */
+        const bool heavy = b.r0 >= 0 && tr == b.r0 / HIMM_TILE && tc == b.c0 / HIMM_TILE;
+        if (heavy) a.worklist[atomicAdd(&a.counters[0], 1)] = rt;
+        else a.worklist[a.worklist_cap - 1 - atomicAdd(&a.counters[3], 1)] = rt;
+      }
     }
   }
 }
@@ -538,7 +546,8 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
   const int n_tiles = a.tiles_r * a.tiles_c;
   /* float4 path: every column segment of a tile is 16-byte aligned and a whole number of quads */
   const bool vec_ok = (rows & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.layer) & 15) == 0);
-  const int n_work = *reinterpret_cast<volatile int*>(&a.counters[0]); /* final: the prep kernel has completed */
+  const int n_heavy = *reinterpret_cast<volatile int*>(&a.counters[0]); /* final: the prep kernel has completed */
+  const int n_work = n_heavy + *reinterpret_cast<volatile int*>(&a.counters[3]);
 
   /* ---- persistent loop: warps pull (robot, tile) work items until the list is empty ---- */
   for (;;) {
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
   if (lane == 0) w = atomicAdd(&a.counters[1], 1);
   w = __shfl_sync(0xffffffffu, w, 0);
   if (w >= n_work) break;
-  const int rt = a.worklist[w];
+  const int rt = a.worklist[w < n_heavy ? w : a.worklist_cap - 1 - (w - n_heavy)];
   const int rel = rt / n_tiles, tile_id = rt - rel * n_tiles;
   const int robot = a.robot0 + rel;
   const int tile_r = tile_id % a.tiles_r, tile_c = tile_id / a.tiles_r;
@@ -800,6 +809,7 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
       a.counters[0] = 0;
       a.counters[1] = 0;
       a.counters[2] = 0;
+      a.counters[3] = 0;
     }
   }
 }
