@@ -451,36 +451,34 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           else view.clear_seq(o, group, marks);
         }
       };
-      /* two steps (two disjoint rings of cells) per iteration */
-      for (int it = tmax - tmin; it >= 0; it -= 2, k += 2) {
-        const bool onA = (unsigned)k <= span, onB = (unsigned)(k + 1) <= span;
-        int offB = off, remB = rem;
-        if ((unsigned)k < span) { /* my next cell (stay on the last one) */
-          remB += my_add;
-          offB += my_dm;
-          if (remB >= my_den) {
-            remB -= my_den;
-            offB += my_dn;
+      /* RINGS steps (disjoint rings of cells) per iteration */
+      constexpr int RINGS = 4;
+      for (int it = tmax - tmin; it >= 0; it -= RINGS, k += RINGS) {
+        int offs[RINGS];
+        bool sens = false;
+#pragma unroll
+        for (int r = 0; r < RINGS; r++) {
+          offs[r] = off;
+          const bool on = (unsigned)(k + r) <= span;
+          sens = sens || (on && (view.sensitive(off) || k + r == mark_k));
+          if ((unsigned)(k + r) < span) { /* my next cell (stay on the last one) */
+            rem += my_add;
+            off += my_dm;
+            if (rem >= my_den) {
+              rem -= my_den;
+              off += my_dn;
+            }
           }
         }
-        const bool sens = (onA && (view.sensitive(off) || k == mark_k)) ||
-                          (onB && (view.sensitive(offB) || k + 1 == mark_k));
         if (!__any_sync(0xffffffffu, sens)) {
-          if (onA) view.set_free(off);
-          if (onB) view.set_free(offB);
+#pragma unroll
+          for (int r = 0; r < RINGS; r++)
+            if ((unsigned)(k + r) <= span) view.set_free(offs[r]);
         } else {
-          ring_exact(onA, off, k == mark_k);
-          __syncwarp();
-          ring_exact(onB, offB, k + 1 == mark_k);
-        }
-        off = offB;
-        rem = remB;
-        if ((unsigned)(k + 1) < span) {
-          rem += my_add;
-          off += my_dm;
-          if (rem >= my_den) {
-            rem -= my_den;
-            off += my_dn;
+#pragma unroll
+          for (int r = 0; r < RINGS; r++) {
+            ring_exact((unsigned)(k + r) <= span, offs[r], k + r == mark_k);
+            __syncwarp();
           }
         }
         __syncwarp();
