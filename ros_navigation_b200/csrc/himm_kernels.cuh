@@ -470,6 +470,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
             }
           }
         }
+        __syncwarp(); /* all reads of this iteration are done before any lane writes (memory-model order) */
         if (!__any_sync(0xffffffffu, sens)) {
 #pragma unroll
           for (int r = 0; r < RINGS; r++)

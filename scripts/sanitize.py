@@ -1,0 +1,30 @@
+"""Small mixed workload for compute-sanitizer (memcheck / racecheck): HIMM fan + general + foreign tiles, moves, VFH."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from oracle import oracle as O
+from ros_navigation_b200 import VFH, DeviceGridMap, capi
+from tests.util import lidar_samples, random_samples, assert_layers_equal
+
+ctx = capi.Context(0)
+rng = np.random.default_rng(0)
+g = O.make_geom(10.0, 6.5, 0.05)
+dg = DeviceGridMap(ctx, (10.0, 6.5), 0.05, n_robots=2, layers=("laser",))
+dg.alias("master", "laser")
+lay = [O.new_layer(g), O.new_layer(g)]
+lay[1][:] = (rng.random(lay[1].shape) * 300).astype(np.float32)
+dg.upload("laser", lay[1], robot=1)
+v = VFH(ctx, n_robots=2)
+for it in range(3):
+    per = [lidar_samples(rng, g, (0.3, 0.1), 700, 0.2, 4.0, clear_frac=0.1), random_samples(rng, g, 300)]
+    off = np.array([0, len(per[0]), len(per[0]) + len(per[1])], np.int32)
+    dg.himm_update_batched("laser", np.concatenate(per), off)
+    for r in range(2):
+        O.himm_update(g, lay[r], per[r])
+    inp = np.zeros(2, capi.VFH_INPUT_DTYPE)
+    inp["x"], inp["y"], inp["yaw"], inp["dt"] = [0.3, -1.0], [0.1, 0.5], [0.2, 2.0], 0.2
+    inp["goal_direction"], inp["goal_distance"], inp["goal_tolerance"] = 90.0, 2000.0, 250.0
+    v.update_batched(dg, "master", inp)
+for r in range(2):
+    assert_layers_equal(dg.download("laser", robot=r), lay[r], "robot %d" % r)
+print("sanitize workload OK")
