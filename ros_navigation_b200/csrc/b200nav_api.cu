@@ -48,6 +48,8 @@ struct b200nav_ctx {
   int64_t launches = 0;
   int sm_count = 0;
   bool profiling = false;
+  cudaStream_t copy_stream = nullptr;      /* host->device copies pipelined with the prep kernel */
+  std::vector<cudaEvent_t> copy_events;
   ProfSlot prof[PROF_KINDS];
   char err[512] = {0};
 };
@@ -268,12 +270,10 @@ struct CloudIn {
   const uint8_t* clear_end = nullptr;
 };
 
-int himm_launch(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
-                int robot0, int n_active, int single_n, int total, int max_per_robot, CloudIn cloud = CloudIn()) {
+int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
+               int robot0, int n_active, int single_n, int total, int max_per_robot, CloudIn cloud, HimmArgs& a) {
   b200nav_ctx* ctx = g->ctx;
-  if (total <= 0) return B200NAV_OK;
   CUDA_TRY(ctx, g->segs.reserve(sizeof(BeamSeg) * (size_t)total));
-  HimmArgs a;
   a.dims = g->dims;
   a.geom = g->geom_dev;
   a.layer = lay->dev;
@@ -288,6 +288,10 @@ int himm_launch(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, 
   a.n_active = n_active;
   a.single_n = single_n;
   a.total = total;
+  a.beam_lo = 0;
+  a.beam_hi = total;
+  a.rel_lo = 0;
+  a.rel_hi = n_active;
   a.tiles_r = (g->dims.rows + TileCfg::kTileR - 1) / TileCfg::kTileR;
   a.tiles_c = (g->dims.cols + TileCfg::kTileC - 1) / TileCfg::kTileC;
   a.chunk_beams = std::min(HIMM_CHUNK, std::max(32, (max_per_robot + 31) & ~31));
@@ -304,21 +308,46 @@ int himm_launch(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, 
   a.counters = static_cast<int*>(g->counters.p);
   a.worklist_cap = (int)n_robot_tiles;
   g->last_total = total;
+  return B200NAV_OK;
+}
+
+/* K0 for beams [beam_lo, beam_hi) of robots [rel_lo, rel_hi) */
+int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int rel_lo, int rel_hi) {
+  b200nav_ctx* ctx = g->ctx;
+  if (beam_hi <= beam_lo) return B200NAV_OK;
+  a.beam_lo = beam_lo;
+  a.beam_hi = beam_hi;
+  a.rel_lo = rel_lo;
+  a.rel_hi = rel_hi;
   {
     ProfScope ps(ctx, PROF_HIMM_PREP);
-    himm_prep_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(a);
+    himm_prep_kernel<<<(beam_hi - beam_lo + 127) / 128, 128, 0, ctx->stream>>>(a);
   }
-  rc = check_launch(ctx, "himm_prep_kernel");
-  if (rc) return rc;
+  return check_launch(ctx, "himm_prep_kernel");
+}
+
+int himm_launch_tile(b200nav_grid* g, const HimmArgs& a) {
+  b200nav_ctx* ctx = g->ctx;
   auto kern = himm_tile_kernel<kSub, kListCap>;
   /* persistent: as many one-warp CTAs as can be resident (32 per SM), never more than there are tiles */
-  dim3 grid((unsigned)std::min<size_t>(n_robot_tiles, (size_t)ctx->sm_count * 32));
+  dim3 grid((unsigned)std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * 32));
   {
     ProfScope ps(ctx, PROF_HIMM_TILE);
     const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
     kern<<<grid, TileCfg::kThreads, smem, ctx->stream>>>(a);
   }
   return check_launch(ctx, "himm_tile_kernel");
+}
+
+int himm_launch(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
+                int robot0, int n_active, int single_n, int total, int max_per_robot, CloudIn cloud = CloudIn()) {
+  if (total <= 0) return B200NAV_OK;
+  HimmArgs a;
+  int rc = himm_setup(g, lay, dev_samples, dev_offsets, robot0, n_active, single_n, total, max_per_robot, cloud, a);
+  if (rc) return rc;
+  rc = himm_launch_prep(g, a, 0, total, 0, n_active);
+  if (rc) return rc;
+  return himm_launch_tile(g, a);
 }
 
 /* Reports (and clears) the device-side "more samples than declared" flag; call after a stream sync. */
@@ -513,6 +542,8 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
       cudaEventDestroy(p.first);
       cudaEventDestroy(p.second);
     }
+  for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200NAV_OK;
@@ -915,7 +946,6 @@ int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const 
   CUDA_TRY(ctx, g->samples.reserve(sizeof(float) * 2 * (size_t)total));
   CUDA_TRY(ctx, g->offsets.reserve(sizeof(int32_t) * (size_t)(nr + 1)));
   CUDA_TRY(ctx, g->origins.reserve(sizeof(double) * 2 * (size_t)nr));
-  CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_xy, sizeof(float) * 2 * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(g->offsets.p, host_offsets, sizeof(int32_t) * (size_t)(nr + 1), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(g->origins.p, host_origins, sizeof(double) * 2 * (size_t)nr, cudaMemcpyHostToDevice, ctx->stream));
   CloudIn c;
@@ -923,10 +953,42 @@ int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const 
   c.xy = static_cast<const float*>(g->samples.p);
   if (host_clear_end) {
     CUDA_TRY(ctx, g->clearbuf.reserve((size_t)total));
-    CUDA_TRY(ctx, cudaMemcpyAsync(g->clearbuf.p, host_clear_end, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
     c.clear_end = static_cast<const uint8_t*>(g->clearbuf.p);
   }
-  int rc = himm_launch(g, l, nullptr, static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per, c);
+  HimmArgs a;
+  int rc = himm_setup(g, l, nullptr, static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per, c, a);
+  if (rc) return rc;
+  /* Pipeline: the cloud is copied in groups of robots on a second stream while the prep kernel of the previous
+   * group runs; the tile kernel starts when everything is binned. */
+  const int groups = (total >= (1 << 16) && nr >= 8) ? 4 : 1;
+  if (groups > 1 && !ctx->copy_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctx->copy_events.resize(8);
+    for (auto& e : ctx->copy_events) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  cudaStream_t cs = groups > 1 ? ctx->copy_stream : ctx->stream;
+  if (groups > 1) { /* the copy stream must not overwrite staging buffers still read by earlier work */
+    CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[7], ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->copy_events[7], 0));
+  }
+  for (int gi = 0; gi < groups; gi++) {
+    const int r_lo = (int)((long long)nr * gi / groups), r_hi = (int)((long long)nr * (gi + 1) / groups);
+    const int b_lo = host_offsets[r_lo], b_hi = host_offsets[r_hi];
+    if (b_hi > b_lo) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(static_cast<float*>(g->samples.p) + 2 * (size_t)b_lo, host_xy + 2 * (size_t)b_lo,
+                                    sizeof(float) * 2 * (size_t)(b_hi - b_lo), cudaMemcpyHostToDevice, cs));
+      if (host_clear_end)
+        CUDA_TRY(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(g->clearbuf.p) + b_lo, host_clear_end + b_lo,
+                                      (size_t)(b_hi - b_lo), cudaMemcpyHostToDevice, cs));
+    }
+    if (groups > 1) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[gi], cs));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[gi], 0));
+    }
+    rc = himm_launch_prep(g, a, b_lo, b_hi, r_lo, r_hi);
+    if (rc) return rc;
+  }
+  rc = himm_launch_tile(g, a);
   if (rc) return rc;
   if (bbox)
     for (int r = 0; r < nr; r++) {

@@ -65,6 +65,9 @@ struct HimmArgs {
   int n_active;                   /* robots handled by this launch                */
   int single_n;                   /* >= 0: single-robot mode, samples [0, n)      */
   int total;                      /* total samples                                */
+  /* the prep kernel may be launched per group of robots (pipelined with the host->device copies):
+   * it then handles beams [beam_lo, beam_hi) which belong to robots [rel_lo, rel_hi) of this update */
+  int beam_lo, beam_hi, rel_lo, rel_hi;
   int tiles_r, tiles_c;           /* tiles per grid                               */
   int n_chunks;                   /* chunks per robot                             */
   int chunk_beams;                /* beams per chunk: multiple of 32, <= HIMM_CHUNK */
@@ -81,29 +84,29 @@ struct HimmArgs {
  * run's (contiguous) bits.  ~10x fewer L2 reductions than one per (beam, tile).
  * ------------------------------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = a.beam_lo + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool valid = i < a.total;
+  const bool valid = i < a.beam_hi;
   int rel = 0, beg = 0;
   if (a.single_n < 0) {
     /* robot of beam i = last r with offsets[r] <= i.  Lane 0 of the warp resolves the warp's first beam
      * (proportional first guess - robots usually carry similar beam counts -, a short linear walk, a binary search
      * only if the walk does not settle), then every lane walks forward from there. */
-    const int i0 = min(i, a.total - 1);
-    int lo = 0;
+    const int i0 = min(i, a.beam_hi - 1);
+    int lo = a.rel_lo;
     if (lane == 0) {
-      lo = (int)(((long long)i0 * a.n_active) / a.total);
+      lo = a.rel_lo + (int)(((long long)(i0 - a.beam_lo) * (a.rel_hi - a.rel_lo)) / (a.beam_hi - a.beam_lo));
       int steps = 0;
-      while (lo > 0 && __ldg(&a.offsets[lo]) > i0 && steps < 6) {
+      while (lo > a.rel_lo && __ldg(&a.offsets[lo]) > i0 && steps < 6) {
         lo--;
         steps++;
       }
-      while (lo + 1 < a.n_active && __ldg(&a.offsets[lo + 1]) <= i0 && steps < 6) {
+      while (lo + 1 < a.rel_hi && __ldg(&a.offsets[lo + 1]) <= i0 && steps < 6) {
         lo++;
         steps++;
       }
-      if (__ldg(&a.offsets[lo]) > i0 || (lo + 1 < a.n_active && __ldg(&a.offsets[lo + 1]) <= i0)) {
-        int l2 = 0, hi = a.n_active;
+      if (__ldg(&a.offsets[lo]) > i0 || (lo + 1 < a.rel_hi && __ldg(&a.offsets[lo + 1]) <= i0)) {
+        int l2 = a.rel_lo, hi = a.rel_hi;
         while (hi - l2 > 1) {
           const int mid = (l2 + hi) >> 1;
           if (__ldg(&a.offsets[mid]) <= i0) l2 = mid;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
     }
     lo = __shfl_sync(0xffffffffu, lo, 0);
     int nxt = __ldg(&a.offsets[lo + 1]);
-    while (nxt <= i0 && lo + 1 < a.n_active) {
+    while (nxt <= i0 && lo + 1 < a.rel_hi) {
       lo++;
       nxt = __ldg(&a.offsets[lo + 1]);
     }

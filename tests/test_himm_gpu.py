@@ -223,6 +223,34 @@ def test_cloud_form_matches_sample_form(ctx):
     dg.close()
 
 
+def test_cloud_form_pipelined_copy_groups(ctx):
+    """Large host-side cloud batches are copied in groups of robots on a second stream, pipelined with the prep kernel
+    (>= 65536 points and >= 8 robots): same result, ragged groups included."""
+    rng = np.random.default_rng(16)
+    n_robots = 100
+    g, dg = make_pair(ctx, 12.8, 12.8, 0.05, n_robots=n_robots)
+    layers = [O.new_layer(g) for _ in range(n_robots)]
+    for cycle in range(2):
+        counts = [(1080, 0, 1500, 700, 1080, 3)[(r + cycle) % 6] for r in range(n_robots)]
+        offsets = np.zeros(n_robots + 1, np.int32)
+        offsets[1:] = np.cumsum(counts)
+        assert offsets[-1] >= 65536
+        origins = rng.uniform(-3, 3, (n_robots, 2))
+        ang = rng.uniform(-np.pi, np.pi, offsets[-1])
+        rad = rng.uniform(0.2, 6.0, offsets[-1])
+        own = np.repeat(np.arange(n_robots), counts)
+        xy = np.stack([origins[own, 0] + rad * np.cos(ang), origins[own, 1] + rad * np.sin(ang)], 1).astype(np.float32)
+        clear = (rng.random(offsets[-1]) < 0.05).astype(np.uint8)
+        dg.himm_update_cloud_batched("laser", origins, xy, clear, offsets)
+        for r in range(0, n_robots, 3):
+            sl = slice(offsets[r], offsets[r + 1])
+            s = O.make_samples(np.full(counts[r], origins[r, 0]), np.full(counts[r], origins[r, 1]),
+                               xy[sl, 0].astype(np.float64), xy[sl, 1].astype(np.float64), clear[sl])
+            O.himm_update(g, layers[r], s)
+            assert_layers_equal(dg.download("laser", robot=r), layers[r], "cycle %d robot %d" % (cycle, r))
+    dg.close()
+
+
 def test_c2_sized_grid_scan_sequence(ctx):
     """BASELINE config 2 geometry: 2048 x 2048 @ 5 cm, 1080-beam / 270 deg scans up to 30 m."""
     import torch
