@@ -37,11 +37,32 @@ class CommandExchange:
         self.n_local = self.hi - self.lo
         self.max_local = -(-total // self.world)
         self.even = total % self.world == 0
-        self.local = torch.zeros(self.n_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
-        self.table = torch.zeros(total, COMMAND_BYTES, dtype=torch.uint8, device=device)
+        # double-buffered so that the gather of cycle k can overlap the kernels of cycle k+1
+        self.locals = [torch.zeros(self.n_local, COMMAND_BYTES, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.tables = [torch.zeros(total, COMMAND_BYTES, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.local, self.table = self.locals[0], self.tables[0]
+        self._pending = [None, None]
         if not self.even:  # padded staging so that every rank contributes the same number of bytes
             self._send = torch.zeros(self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
             self._recv = torch.zeros(self.world * self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
+
+    def gather_async(self, slot):
+        """Start the all-gather of `self.locals[slot]` into `self.tables[slot]` without blocking the caller's stream:
+        the collective runs on the backend's own stream after the work already enqueued (NCCL), so it overlaps the
+        next cycle's kernels.  Call wait(slot) before reading tables[slot] or rewriting locals[slot]."""
+        self.wait(slot)
+        if self.world == 1:
+            self.tables[slot].copy_(self.locals[slot])
+            return
+        assert self.even, "gather_async needs total % world == 0"
+        self._pending[slot] = dist.all_gather_into_tensor(self.tables[slot].view(-1), self.locals[slot].view(-1),
+                                                          group=self.group, async_op=True)
+
+    def wait(self, slot=None):
+        for s in ([slot] if slot is not None else [0, 1]):
+            if self._pending[s] is not None:
+                self._pending[s].wait()
+                self._pending[s] = None
 
     def gather(self):
         """All ranks call this once per cycle after their VFH+ kernel wrote `self.local`. Returns `self.table`."""

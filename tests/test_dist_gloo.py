@@ -58,6 +58,20 @@ def _worker(rank, world, port, total, out_dir):
             assert np.array_equal(table["picked_angle"], (allr * 0.5).astype(np.float32))
             owners = np.array([D.owner_of(r, total, world) for r in allr])
             assert np.array_equal(table["flags"], owners)
+        if ex.even:  # asynchronous, double-buffered form used by the pipelined batched mode
+            for cycle in range(4):
+                slot = cycle & 1
+                ex.wait(slot)
+                cmd = np.zeros(ex.n_local, COMMAND_DTYPE)
+                cmd["speed"] = np.arange(ex.lo, ex.hi) + 1000 * cycle
+                ex.locals[slot].copy_(torch.from_numpy(cmd.view(np.uint8).reshape(ex.n_local, 16)))
+                ex.gather_async(slot)
+                if cycle >= 1:  # read the previous cycle's table while this one is in flight
+                    prev = 1 - slot
+                    ex.wait(prev)
+                    t = ex.tables[prev].numpy().copy().view(COMMAND_DTYPE).reshape(-1)
+                    assert np.array_equal(t["speed"], np.arange(total) + 1000 * (cycle - 1))
+            ex.wait()
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
