@@ -100,6 +100,15 @@ int b200nav_grid_move(b200nav_grid* grid, int robot, double x, double y, int* mo
  * reversed cell order, unwrapped index.  out_host = rows*cols bytes. */
 int b200nav_grid_to_occupancy(b200nav_grid* grid, int robot, const char* layer, float data_min, float data_max,
                               int8_t* out_host);
+/* MapGlobalPlanner::ifBlocked (move_control/include/move_control/map_global_planner.h:39-54, grid_map::CircleIterator)
+ * for n query points (host_xy: n*2 doubles): out_host[i] = 1 if any cell whose centre lies within `radius` of the
+ * point holds a non-NaN value > 0.  The RRT planner (rrt_planner.cpp:53) can test candidates against the
+ * device-resident master layer without downloading it. */
+int b200nav_grid_query_blocked(b200nav_grid* grid, int robot, const char* layer, const double* host_xy, int n,
+                               double radius, uint8_t* out_host);
+/* Tell the library that layer `layer` was written through b200nav_grid_layer_devptr (robot < 0: all robots); it drops
+ * the cached per-tile knowledge the HIMM kernel keeps about that layer. */
+int b200nav_grid_layer_written(b200nav_grid* grid, const char* layer, int robot);
 /* Device pointer of a layer ([robot][col][row] floats) for zero-copy consumers. */
 void* b200nav_grid_layer_devptr(b200nav_grid* grid, const char* layer);
 

@@ -88,6 +88,13 @@ class GridLayers {
   int toOccupancyGrid(const std::string& layer, float data_min, float data_max, int8_t* out, int robot = 0) {
     return b200nav_grid_to_occupancy(grid_, robot, layer.c_str(), data_min, data_max, out);
   }
+  /* MapGlobalPlanner::ifBlocked (map_global_planner.h:39-54) against the device layer */
+  bool ifBlocked(double x, double y, double radius = 0.3, const std::string& layer = "master", int robot = 0) {
+    const double xy[2] = {x, y};
+    uint8_t out = 0;
+    b200nav_grid_query_blocked(grid_, robot, layer.c_str(), xy, 1, radius, &out);
+    return out != 0;
+  }
   int rows() const { return rows_; }
   int cols() const { return cols_; }
   b200nav_grid* get() const { return grid_; }

@@ -537,6 +537,37 @@ void oracle_to_occupancy(const oracle_geom* g, const float* layer, float data_mi
   }
 }
 
+int oracle_if_blocked(const oracle_geom* g, const float* master, double x, double y, double radius) {
+  /* CircleIterator::findSubmapParameters (CircleIterator.cpp:99-113) */
+  const double radius_square = pow(radius, 2);
+  double tlx = x + radius, tly = y + radius, brx = x - radius, bry = y - radius;
+  limit_position_to_range(tlx, tly, g->len_x, g->len_y, g->pos_x, g->pos_y);
+  limit_position_to_range(brx, bry, g->len_x, g->len_y, g->pos_x, g->pos_y);
+  int sr, sc, er, ec;
+  if (!geom_index(g, tlx, tly, sr, sc) || !geom_index(g, brx, bry, er, ec)) return 0;
+  /* getSubmapSizeFromCornerIndeces (GridMapMath.cpp:298-304): unwrapped corner difference + 1 */
+  int usr = sr, usc = sc, uer = er, uec = ec;
+  index_from_buffer_index(g, usr, usc);
+  index_from_buffer_index(g, uer, uec);
+  const int nr = uer - usr + 1, nc = uec - usc + 1;
+  /* SubmapIterator walks the nr x nc block; ifBlocked returns at the first hit, i.e. "any" */
+  for (int i = 0; i < nr; i++)
+    for (int j = 0; j < nc; j++) {
+      int b0 = usr + i, b1 = usc + j;
+      buffer_index_from_index(g, b0, b1);
+      double px, py;
+      if (!position_from_index(b0, b1, g->len_x, g->len_y, g->pos_x, g->pos_y, g->res, g->rows, g->cols, g->start0,
+                               g->start1, px, py))
+        continue;
+      const double dx = px - x, dy = py - y;
+      if (!(dx * dx + dy * dy <= radius_square)) continue; /* CircleIterator::isInside (:90-97) */
+      const float v = master[static_cast<size_t>(b1) * g->rows + b0];
+      if (std::isnan(v)) continue;
+      if (v > 0.0) return 1;
+    }
+  return 0;
+}
+
 void oracle_goal_from_pose(double rx, double ry, double yaw, double tx, double ty, float* desired_angle,
                            float* desired_dist) {
   /* steerer.cpp:228-256: float deltaX/deltaY/desiredDist; hypot on floats; RAD2DEG(normalize_angle_positive()) */

@@ -68,6 +68,7 @@ def lib():
         L.oracle_move.argtypes = [gp, C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_double]
         L.oracle_to_occupancy.argtypes = [gp, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         L.oracle_goal_from_pose.argtypes = [C.c_double] * 5 + [_fp, _fp]
+        L.oracle_if_blocked.argtypes = [gp, C.c_void_p, C.c_double, C.c_double, C.c_double]
         _lib = L
     return _lib
 
@@ -203,6 +204,10 @@ def to_occupancy(g, layer, data_min=0.0, data_max=255.0):
     out = np.zeros(g.rows * g.cols, dtype=np.int8)
     lib().oracle_to_occupancy(C.byref(g), layer.ctypes.data, data_min, data_max, out.ctypes.data)
     return out
+
+
+def if_blocked(g, master, x, y, radius=0.3):
+    return bool(lib().oracle_if_blocked(C.byref(g), master.ctypes.data, x, y, radius))
 
 
 def goal_from_pose(rx, ry, yaw, tx, ty):

@@ -85,6 +85,11 @@ int oracle_move(oracle_geom* g, float** layers, int nlayers, double x, double y)
 void oracle_to_occupancy(const oracle_geom* g, const float* layer, float data_min, float data_max,
                          signed char* out);
 
+/* MapGlobalPlanner::ifBlocked (move_control/include/move_control/map_global_planner.h:39-54) over
+ * grid_map::CircleIterator (grid_map_core/src/iterators/CircleIterator.cpp:17-37,80-113): 1 if any cell whose centre
+ * lies within `radius` of (x, y) holds a non-NaN value > 0. */
+int oracle_if_blocked(const oracle_geom* g, const float* master, double x, double y, double radius);
+
 /* Steerer::update goal geometry (steerer.cpp:232-256): desiredDist (mm), desiredAngle (deg). */
 void oracle_goal_from_pose(double rx, double ry, double yaw, double tx, double ty,
                            float* desired_angle, float* desired_dist);

@@ -65,6 +65,8 @@ _SIGNATURES = {
                                             C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200nav_grid_move": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int)]),
     "b200nav_grid_to_occupancy": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_float, C.c_float, C.c_void_p]),
+    "b200nav_grid_query_blocked": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    "b200nav_grid_layer_written": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "b200nav_grid_layer_devptr": (C.c_void_p, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_update": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200nav_himm_update_batched": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -857,6 +857,35 @@ int b200nav_grid_to_occupancy(b200nav_grid* g, int robot, const char* layer, flo
   return sync_stream(g->ctx);
 }
 
+int b200nav_grid_query_blocked(b200nav_grid* g, int robot, const char* layer, const double* host_xy, int n,
+                               double radius, uint8_t* out_host) {
+  if (!g || robot < 0 || robot >= g->n_robots || n < 0 || (n > 0 && (!host_xy || !out_host)) || !(radius >= 0))
+    return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  if (n == 0) return B200NAV_OK;
+  b200nav_ctx* ctx = g->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, g->samples.reserve(sizeof(double) * 2 * (size_t)n));
+  CUDA_TRY(ctx, g->occ.reserve((size_t)n));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_xy, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t per = (size_t)g->dims.rows * g->dims.cols;
+  grid_blocked_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+      g->dims, g->geom_host[robot], l->dev + per * robot, static_cast<const double*>(g->samples.p), n, radius,
+      static_cast<uint8_t*>(g->occ.p));
+  int rc = check_launch(ctx, "grid_blocked_kernel");
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_host, g->occ.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_stream(ctx);
+}
+
+int b200nav_grid_layer_written(b200nav_grid* g, const char* layer, int robot) {
+  if (!g || robot >= g->n_robots) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  return reset_free_cols(g, l, robot);
+}
+
 void* b200nav_grid_layer_devptr(b200nav_grid* g, const char* layer) {
   if (!g) return nullptr;
   Layer* l = find_layer(g, layer);

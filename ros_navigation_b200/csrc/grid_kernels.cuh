@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "geometry.h"
+
 namespace b200nav {
 
 __global__ void grid_fill_kernel(float* __restrict__ p, size_t n, float value) {
@@ -42,6 +44,55 @@ __global__ void grid_to_occupancy_kernel(const float* __restrict__ layer, int ro
   if (u1 < 0) u1 += cols;
   const size_t index = (size_t)u1 * rows + u0;
   out[n - index - 1] = (int8_t)value;
+}
+
+/* MapGlobalPlanner::ifBlocked for a batch of query points (move_control/include/move_control/map_global_planner.h:
+ * 39-54 over grid_map::CircleIterator, grid_map_core/src/iterators/CircleIterator.cpp): one warp per query, lanes
+ * stride over the cells of the circle's bounding block; out[q] = 1 if any cell centre within `radius` holds a
+ * non-NaN value > 0.  Lets the host-side RRT planner test candidates against the device-resident master layer
+ * without downloading it (rrt_planner.cpp:53). */
+__global__ void grid_blocked_kernel(GridDims d, RobotGeom g, const float* __restrict__ layer,
+                                    const double* __restrict__ xy, int n, double radius, uint8_t* __restrict__ out) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= n) return;
+  const double x = xy[2 * q], y = xy[2 * q + 1];
+  const double r2 = radius * radius;
+  double tlx = x + radius, tly = y + radius, brx = x - radius, bry = y - radius;
+  limit_position_to_range(tlx, tly, d.len_x, d.len_y, g.pos_x, g.pos_y);
+  limit_position_to_range(brx, bry, d.len_x, d.len_y, g.pos_x, g.pos_y);
+  int sr, sc, er, ec;
+  bool hit = false;
+  if (grid_index(d, g, tlx, tly, sr, sc) && grid_index(d, g, brx, bry, er, ec)) {
+    if ((g.start0 | g.start1) != 0) {
+      sr -= g.start0;
+      sc -= g.start1;
+      er -= g.start0;
+      ec -= g.start1;
+      wrap_index(sr, d.rows);
+      wrap_index(sc, d.cols);
+      wrap_index(er, d.rows);
+      wrap_index(ec, d.cols);
+    }
+    const int nr = er - sr + 1, nc = ec - sc + 1;
+    for (int k = lane; k < nr * nc && nr > 0 && nc > 0; k += 32) {
+      int b0 = sr + k % nr, b1 = sc + k / nr;
+      if (b0 < 0 || b1 < 0 || b0 >= d.rows || b1 >= d.cols) continue;
+      if ((g.start0 | g.start1) != 0) {
+        b0 += g.start0;
+        b1 += g.start1;
+        wrap_index(b0, d.rows);
+        wrap_index(b1, d.cols);
+      }
+      double px, py;
+      position_from_index(b0, b1, d.len_x, d.len_y, g.pos_x, g.pos_y, d.res, d.rows, d.cols, g.start0, g.start1, px, py);
+      const double dx = px - x, dy = py - y;
+      if (!(dx * dx + dy * dy <= r2)) continue;
+      const float v = layer[(size_t)b1 * d.rows + b0];
+      if (v > 0.0f) hit = true; /* false for NaN */
+    }
+  }
+  const unsigned any = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) out[q] = any ? 1 : 0;
 }
 
 }  // namespace b200nav

@@ -75,6 +75,17 @@ class DeviceGridMap:
               self.ctx.h)
         return out
 
+    def query_blocked(self, points, radius=0.3, layer="master", robot=0):
+        """MapGlobalPlanner::ifBlocked for an array of points [n,2] -> bool[n] (map_global_planner.h:39-54)."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros(len(pts), np.uint8)
+        check(lib().b200nav_grid_query_blocked(self.h, robot, layer.encode(), pts.ctypes.data, len(pts), float(radius),
+                                               out.ctypes.data), self.ctx.h)
+        return out.astype(bool)
+
+    def layer_written(self, layer, robot=-1):
+        check(lib().b200nav_grid_layer_written(self.h, layer.encode(), int(robot)), self.ctx.h)
+
     def layer_devptr(self, layer):
         return lib().b200nav_grid_layer_devptr(self.h, layer.encode())
 

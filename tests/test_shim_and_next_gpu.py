@@ -94,6 +94,28 @@ def test_to_occupancy_grid(ctx):
         dg.close()
 
 
+def test_query_blocked_matches_if_blocked(ctx):
+    """MapGlobalPlanner::ifBlocked (map_global_planner.h:39-54) as the RRT planner uses it (rrt_planner.cpp:53)."""
+    from ros_navigation_b200 import DeviceGridMap
+    rng = np.random.default_rng(13)
+    for geom, start in [((10.0, 10.0, 0.05, 0.0, 0.0), (0, 0)), ((4.0, 4.0, 0.05, 1.3, -0.7), (17, 63))]:
+        g = O.make_geom(*geom, start)
+        dg = DeviceGridMap(ctx, geom[:2], geom[2], geom[3:5], layers=("master",))
+        dg.set_geometry(0, geom[3:5], start)
+        layer = O.new_layer(g)
+        m = rng.random(layer.shape)
+        layer[m < 0.4] = 0.0
+        layer[(m >= 0.4) & (m < 0.405)] = rng.choice([10.0, 90.0, 180.0], ((m >= 0.4) & (m < 0.405)).sum())
+        dg.upload("master", layer)
+        pts = np.stack([geom[3] + (rng.random(400) - 0.5) * geom[0] * 1.2, geom[4] + (rng.random(400) - 0.5) * geom[1] * 1.2], 1)
+        for radius in (0.3, 0.07, 1.0):
+            got = dg.query_blocked(pts, radius)
+            want = np.array([O.if_blocked(g, layer, p[0], p[1], radius) for p in pts])
+            assert np.array_equal(got, want), "radius %g: %d differ" % (radius, (got != want).sum())
+            assert want.any() and not want.all()
+        dg.close()
+
+
 def test_error_paths(ctx):
     """Error behaviour of the C ABI: unknown layer, bad robot index, bad arguments -> negative codes, no crash."""
     from ros_navigation_b200 import DeviceGridMap, capi
