@@ -83,7 +83,7 @@ struct HimmArgs {
  * word equals its left neighbour's joins that neighbour's run, and the head of each run issues one RED.OR with the
  * run's (contiguous) bits.  ~10x fewer L2 reductions than one per (beam, tile).
  * ------------------------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(128) himm_prep_kernel(HimmArgs a) {
+__global__ void __launch_bounds__(128, 12) himm_prep_kernel(HimmArgs a) {
   const int i = a.beam_lo + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool valid = i < a.beam_hi;
