@@ -114,8 +114,7 @@ struct b200nav_grid {
   std::vector<RobotGeom> geom_host;
   RobotGeom* geom_dev = nullptr;
   std::map<std::string, Layer> layers;
-  DevBuf samples, segs, offsets, occ, stats, beam_masks, col_masks, errflag, origins, clearbuf, touched, worklist, counters;
-  size_t masks_zeroed_bytes = 0, colmasks_zeroed_bytes = 0;
+  DevBuf samples, segs, offsets, occ, stats, beam_masks, errflag, origins, clearbuf, touched, worklist, counters;
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
 };
@@ -238,16 +237,11 @@ using TileCfg = HimmTileCfg<kSub, kListCap>;
 /* Binning scratch: grow-only, kept all-zero between updates (the tile kernel clears what it consumes). */
 int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words, size_t n_robot_tiles) {
   b200nav_ctx* ctx = g->ctx;
-  const size_t mb = n_tiles_total * (size_t)mask_words * sizeof(uint32_t), cb = n_tiles_total * sizeof(unsigned long long);
+  const size_t mb = n_tiles_total * (size_t)mask_words * sizeof(uint32_t);
   if (mb > g->beam_masks.cap) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, g->beam_masks.reserve(mb));
     CUDA_TRY(ctx, cudaMemsetAsync(g->beam_masks.p, 0, g->beam_masks.cap, ctx->stream));
-  }
-  if (cb > g->col_masks.cap) {
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(ctx, g->col_masks.reserve(cb));
-    CUDA_TRY(ctx, cudaMemsetAsync(g->col_masks.p, 0, g->col_masks.cap, ctx->stream));
   }
   if (!g->errflag.p) {
     CUDA_TRY(ctx, g->errflag.reserve(sizeof(int)));
@@ -640,7 +634,6 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   g->occ.release();
   g->stats.release();
   g->beam_masks.release();
-  g->col_masks.release();
   g->errflag.release();
   g->origins.release();
   g->clearbuf.release();
