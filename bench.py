@@ -461,10 +461,12 @@ def run_gpu_arm(args, rank, world, local_rank):
         except Exception as e:  # the baseline must never take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
     if world == 1 and args.workload == "c4" and not args.no_extra:
-        try:
-            line["other_workloads"] = {"c2": single_robot_numbers(device, "c2")}
-        except Exception as e:
-            line["other_workloads"] = {"error": repr(e)}
+        line["other_workloads"] = {}
+        for key, fn in (("c2", single_robot_numbers), ("c5", batched_numbers)):
+            try:
+                line["other_workloads"][key] = fn(device, key)
+            except Exception as e:
+                line["other_workloads"][key] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -499,6 +501,40 @@ def single_robot_numbers(device, name, scans=300):
     return {"workload": workload_config(name, 1, 1)["workload"], "value": scans / (dev_ms / 1000.0),
             "e2e": scans / e2e_s, "unit": UNIT, "ms_per_scan": dev_ms / scans, "kernel_ms": kms,
             "l2": "grid (16 MiB) L2-resident"}
+
+
+def batched_numbers(device, name, steps=12):
+    """A second batched configuration (BASELINE config 5: 16384 robots x 256x256) on this GPU: device-resident value
+    and the tile kernel's roofline fraction, measured like the main line (events per step, L2 flushed)."""
+    import numpy as np
+    import torch
+    from ros_navigation_b200 import synth
+    stream = torch.cuda.Stream(device)
+    robots = synth.CONFIGS[name]["robots"]
+    with torch.cuda.stream(stream):
+        arm = GpuArm(name, 0, robots, device, stream, 1)
+        alg = [arm.algorithmic_bytes(c) for c in range(N_CYCLES)]
+        for w in range(12):
+            arm.step_dev(w)
+        stream.synchronize()
+        arm.ctx.profile_enable(True)
+        ms = timed_steps(torch, stream, arm.step_dev, 12, steps, arm)
+        tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
+        arm.ctx.profile_enable(False)
+    peak = 6543.7
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
+    except Exception:
+        pass
+    used = float(np.mean([alg[(12 + k) % N_CYCLES][0] for k in range(steps)]))
+    achieved = used / (tile_ms / max(tile_n, 1) / 1000.0) / 1e9
+    out = {"workload": workload_config(name, 1, robots)["workload"], "value": robots * steps / (sum(ms) / 1000.0),
+           "unit": UNIT, "ms_per_step": sum(ms) / steps,
+           "roofline": {"kernel": "himm_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "avg_launch_ms": tile_ms / max(tile_n, 1)}}
+    del arm
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
