@@ -293,6 +293,10 @@ int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, c
   a.n_chunks = std::max(1, (max_per_robot + a.chunk_beams - 1) / a.chunk_beams);
   const size_t n_tiles_total = (size_t)n_active * a.n_chunks * a.tiles_r * a.tiles_c;
   const size_t n_robot_tiles = (size_t)n_active * a.tiles_r * a.tiles_c;
+  if (n_tiles_total * (size_t)a.mask_words * sizeof(uint32_t) > ((size_t)8 << 30))
+    return set_err(ctx, B200NAV_ERANGE,
+                   "binning scratch would need %zu MiB (robots x samples-per-robot/2048 x tiles): split the update",
+                   (n_tiles_total * (size_t)a.mask_words * sizeof(uint32_t)) >> 20);
   int rc = himm_reserve_masks(g, n_tiles_total, a.mask_words, n_robot_tiles);
   if (rc) return rc;
   a.beam_masks = static_cast<uint32_t*>(g->beam_masks.p);
@@ -900,8 +904,19 @@ int b200nav_himm_update(b200nav_grid* g, int robot, const char* layer, const b20
   CUDA_TRY(ctx, g->samples.reserve(sizeof(b200nav_sample) * (size_t)n));
   CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_samples, sizeof(b200nav_sample) * (size_t)n,
                                 cudaMemcpyHostToDevice, ctx->stream));
-  int rc = himm_launch(g, l, static_cast<const b200nav_sample*>(g->samples.p), nullptr, robot, 1, n, n, n);
-  if (rc) return rc;
+  /* The binning scratch grows with (samples per robot / 2048) x tiles: very long single-robot batches are applied
+   * as several launches over consecutive sample ranges (the order is preserved: launches run back to back). */
+  const size_t tiles = grid_tiles(g);
+  const size_t bytes_per_chunk = tiles * HIMM_MASK_WORDS * sizeof(uint32_t);
+  static const char* budget_env = getenv("B200NAV_MASK_BUDGET_MB"); /* testing aid; default 256 MiB */
+  const size_t budget = (size_t)(budget_env ? std::max(1, atoi(budget_env)) : 256) << 20;
+  const int max_chunks = (int)std::min<size_t>(4096, std::max<size_t>(1, budget / std::max<size_t>(bytes_per_chunk, 1)));
+  const int max_n = max_chunks * HIMM_CHUNK;
+  for (int first = 0; first < n; first += max_n) {
+    const int cnt = std::min(max_n, n - first);
+    int rc = himm_launch(g, l, static_cast<const b200nav_sample*>(g->samples.p) + first, nullptr, robot, 1, cnt, cnt, cnt);
+    if (rc) return rc;
+  }
   if (bbox) host_touch(host_samples, n, bbox); /* overlaps the kernels */
   return sync_stream(ctx);
 }

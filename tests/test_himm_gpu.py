@@ -90,6 +90,35 @@ def test_chunking_more_beams_than_list_capacity(ctx):
     dg.close()
 
 
+def test_very_long_single_batch_is_split():
+    """A single-robot batch whose binning scratch would exceed the budget is applied as consecutive launches.  Run in
+    a child process with a 1 MiB budget (2048 x 2048 grid: 256 KiB of masks per 2048 samples -> 8192 samples per
+    launch) so that 20000 samples need three launches."""
+    import subprocess
+    import sys
+    code = """
+import numpy as np
+from oracle import oracle as O
+from ros_navigation_b200 import DeviceGridMap, capi
+from tests.util import assert_layers_equal, lidar_samples, random_samples
+ctx = capi.Context(0)
+rng = np.random.default_rng(33)
+g = O.make_geom(102.4, 102.4, 0.05)
+dg = DeviceGridMap(ctx, (102.4, 102.4), 0.05, layers=("laser",))
+layer = O.new_layer(g)
+s = np.concatenate([lidar_samples(rng, g, (1.0, -2.0), 17000, 0.5, 20.0, clear_frac=0.1), random_samples(rng, g, 3000, spread=0.3)])
+O.himm_update(g, layer, s)
+dg.himm_update("laser", s)
+assert_layers_equal(dg.download("laser"), layer, "20000 samples")
+print("SPLIT_OK")
+"""
+    import os
+    env = dict(os.environ, B200NAV_MASK_BUDGET_MB="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert "SPLIT_OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_edge_cases(ctx):
     g, dg = make_pair(ctx, 8.0, 5.0, 1.0)
     layer = O.new_layer(g)
