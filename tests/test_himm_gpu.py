@@ -119,6 +119,26 @@ print("SPLIT_OK")
     assert "SPLIT_OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_several_scans_and_sonar_rays_in_one_update(ctx):
+    """One update may carry several messages (different origins) - LaserMapUpdater keeps buffering between updates -
+    and the sonar updaters push one ray per message into layer "range" (range_map_updater.cpp:38-76)."""
+    rng = np.random.default_rng(9)
+    g, dg = make_pair(ctx, 10.0, 10.0, 0.05, layers=("laser", "range"))
+    laser, sonar = O.new_layer(g), O.new_layer(g)
+    for cycle in range(5):
+        parts = [lidar_samples(rng, g, (rng.uniform(-2, 2), rng.uniform(-2, 2)), n, 0.2, 4.0, clear_frac=0.05)
+                 for n in (360, 17, 360, 45)]
+        s = np.concatenate(parts)          # batches of 32 straddle the scans: fan and general schedules interleave
+        O.himm_update(g, laser, s)
+        dg.himm_update("laser", s)
+        rays = random_samples(rng, g, 5 * 4, spread=0.9, clear_frac=0.3)   # 5 sonars, a few messages each
+        O.himm_update(g, sonar, rays)
+        dg.himm_update("range", rays)
+    assert_layers_equal(dg.download("laser"), laser, "laser")
+    assert_layers_equal(dg.download("range"), sonar, "range")
+    dg.close()
+
+
 def test_edge_cases(ctx):
     g, dg = make_pair(ctx, 8.0, 5.0, 1.0)
     layer = O.new_layer(g)

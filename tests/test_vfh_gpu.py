@@ -113,11 +113,55 @@ def run_live(ctx, steps, seed, **kw):
 
 @pytest.mark.parametrize("seed,kw", [(101, dict()), (102, dict()), (103, dict(window_diameter=33)),
                                      (104, dict(window_diameter=129, cell_size=20.0)),
-                                     (105, dict(weight_desired_dir=5.0, weight_current_dir=3.0, max_speed=400))])
+                                     (105, dict(weight_desired_dir=5.0, weight_current_dir=3.0, max_speed=400)),
+                                     (106, dict(sector_angle=10)), (107, dict(sector_angle=3, window_diameter=21)),
+                                     (108, dict(safety_dist_1ms=10.0)),            # one sector table
+                                     (109, dict(max_turnrate_1ms=10, max_speed=1000, robot_radius=250.0))])
 def test_update_ranges_vs_live_reference(ctx, seed, kw):
     if not O.have_ref():
         pytest.skip("oracle/_ref missing")
     run_live(ctx, 80, seed, **kw)
+
+
+def test_flags_and_current_max_speed(ctx):
+    """Emergency stop, hemmed-in and cant-turn paths are exercised and flagged; SetCurrentMaxSpeed (vfh.cpp:144-166)
+    rebuilds the turning-radius table like the reference."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref missing")
+    from ros_navigation_b200 import VFH, capi
+    ref = O.RefVFH()
+    v = VFH(ctx, params_from_dict(ref.params))
+    seen = 0
+    rng = np.random.default_rng(3)
+    free = np.full((361, 2), 5000.0)
+    wall_close = free.copy()
+    wall_close[:, 0] = 120.0           # everything 12 cm away: inside the safety distance -> emergency
+    wall_mid = free.copy()
+    wall_mid[:, 0] = 900.0             # blocked all around but outside the safety distance -> hemmed in
+    for step in range(60):
+        if step == 20:
+            ref.set_current_max_speed(120)
+            v.SetCurrentMaxSpeed(120)
+        r = [free, wall_close, wall_mid, free][step % 4] if step < 40 else free
+        gdist = float(np.float32(rng.uniform(50, 400))) if step >= 40 else 3000.0
+        gdir = float(np.float32(rng.uniform(0, 180)))
+        speed = int(rng.integers(0, 200))
+        rcs, rct = ref.update(r, speed, gdir, gdist, 250.0, 0.2)
+        inp = VFH.make_input(dt=0.2, speed=speed, goal_dir=gdir, goal_dist=gdist, tol=250.0)
+        out = np.zeros(1, capi.COMMAND_DTYPE)
+        capi.check(capi.lib().b200nav_vfh_update_ranges(v.h, 0, np.ascontiguousarray(r).ctypes.data, inp.ctypes.data,
+                                                         out.ctypes.data), ctx.h)
+        assert (int(out["speed"][0]), int(out["turnrate"][0])) == (rcs, rct), "step %d" % step
+        assert float(out["picked_angle"][0]) == ref.state()["picked"]
+        seen |= int(out["flags"][0])
+        if step % 4 == 1 and step < 40:
+            assert int(out["flags"][0]) & capi.CMD_EMERGENCY
+            assert np.array_equal(v.state()["origin_hist"], np.ones(72, np.float32))
+        if step % 4 == 2 and step < 40:
+            assert int(out["flags"][0]) & capi.CMD_HEMMED_IN
+    assert seen & capi.CMD_EMERGENCY and seen & capi.CMD_HEMMED_IN and seen & capi.CMD_CANT_TURN
+    assert np.array_equal(v.tables(0)[4][:121], ref.min_turning_radius())
+    v.close()
 
 
 def make_world_layer(rng, g, density=0.03):
