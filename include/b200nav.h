@@ -109,8 +109,20 @@ int b200nav_grid_query_blocked(b200nav_grid* grid, int robot, const char* layer,
 /* Tell the library that layer `layer` was written through b200nav_grid_layer_devptr (robot < 0: all robots); it drops
  * the cached per-tile knowledge the HIMM kernel keeps about that layer. */
 int b200nav_grid_layer_written(b200nav_grid* grid, const char* layer, int robot);
-/* Device pointer of a layer ([robot][col][row] floats) for zero-copy consumers. */
+/* Device pointer of a layer ([robot][col][row] floats, the reference's Eigen::MatrixXf layout per robot) for
+ * zero-copy consumers.  Layers normally live in HBM as one byte per cell (see b200nav_grid_layer_format); asking for
+ * the raw pointer converts the layer to the float layout for good (slower HIMM updates).  NULL if there is no such
+ * layer. */
 void* b200nav_grid_layer_devptr(b200nav_grid* grid, const char* layer);
+/* GridMap::exists (grid_map_core/src/GridMap.cpp:116-119): 1 if the layer exists, else 0. */
+int b200nav_grid_has_layer(const b200nav_grid* grid, const char* layer);
+/* Device format of a layer.  CODED: one byte per cell in 64 x 64-cell tile records - possible while every value is NaN
+ * or one of 0, 10, ..., 180, which is all the HIMM update ever writes (map_updater.h:49-71).  FLOAT: the reference's
+ * float matrix; a layer switches to it when b200nav_grid_upload brings any other value or the raw device pointer is
+ * requested.  Results are identical in both formats. */
+#define B200NAV_LAYER_FLOAT 0
+#define B200NAV_LAYER_CODED 1
+int b200nav_grid_layer_format(b200nav_grid* grid, const char* layer);
 
 /* ------------------------------------------------------------------------------------------------------
  * HIMM update.  Replaces LaserMapUpdater::updateMap / RangeMapUpdater::updateMap

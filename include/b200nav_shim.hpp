@@ -64,7 +64,7 @@ class GridLayers {
   GridLayers(const GridLayers&) = delete;
   GridLayers& operator=(const GridLayers&) = delete;
 
-  bool exists(const std::string& layer) { return b200nav_grid_layer_devptr(grid_, layer.c_str()) != nullptr; }
+  bool exists(const std::string& layer) { return b200nav_grid_has_layer(grid_, layer.c_str()) != 0; }
   void add(const std::string& layer) { b200nav_grid_add_layer(grid_, layer.c_str()); }
   /* map_["master"] = map_["laser"] (map_provider.cpp:221): copying and zero-copy forms */
   int copyLayer(const std::string& dst, const std::string& src) {

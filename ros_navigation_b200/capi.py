@@ -68,6 +68,8 @@ _SIGNATURES = {
     "b200nav_grid_query_blocked": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "b200nav_grid_layer_written": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "b200nav_grid_layer_devptr": (C.c_void_p, [C.c_void_p, C.c_char_p]),
+    "b200nav_grid_has_layer": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "b200nav_grid_layer_format": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_update": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200nav_himm_update_batched": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200nav_himm_update_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),

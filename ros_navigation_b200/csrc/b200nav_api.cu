@@ -97,12 +97,20 @@ struct DevBuf {
   }
 };
 
+/* One layer of all robots; aliases (b200nav_grid_alias_layer) share the object.  Device format: cells.cuh. */
 struct Layer {
-  float* dev = nullptr;
-  bool owned = true;
-  /* [n_robots * n_tiles] free-column summaries of the HIMM tile kernel (shared with aliases of this layer);
-   * all-zero = nothing known.  Every writer of the layer other than the tile kernel resets it. */
+  void* dev = nullptr;
+  bool coded = true;
+  /* [n_robots * n_tiles] free-column summaries of the HIMM tile kernel; all-zero = nothing known (CODED layers only
+   * ever hold 0 or all-ones: the whole tile is free).  Every writer of the layer other than the tile kernel resets
+   * it. */
   unsigned long long* free_cols = nullptr;
+  float* fdev() const { return static_cast<float*>(dev); }
+  uint8_t* cdev() const { return static_cast<uint8_t*>(dev); }
+  ~Layer() {
+    if (dev) cudaFree(dev);
+    if (free_cols) cudaFree(free_cols);
+  }
 };
 
 }  // namespace
@@ -113,8 +121,9 @@ struct b200nav_grid {
   int n_robots = 1;
   std::vector<RobotGeom> geom_host;
   RobotGeom* geom_dev = nullptr;
-  std::map<std::string, Layer> layers;
+  std::map<std::string, std::shared_ptr<Layer>> layers;
   DevBuf samples, segs, offsets, occ, stats, beam_masks, errflag, origins, clearbuf, touched, worklist, counters;
+  DevBuf stage, convflag; /* float staging for upload / download of CODED layers; conversion "bad value" flag */
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
 };
@@ -196,7 +205,15 @@ void prof_drain(b200nav_ctx* ctx) {
 Layer* find_layer(b200nav_grid* g, const char* name) {
   if (!name) return nullptr;
   auto it = g->layers.find(name);
-  return it == g->layers.end() ? nullptr : &it->second;
+  return it == g->layers.end() ? nullptr : it->second.get();
+}
+
+/* every distinct layer object once (aliases share theirs) */
+std::vector<Layer*> unique_layers(b200nav_grid* g) {
+  std::vector<Layer*> v;
+  for (auto& kv : g->layers)
+    if (std::find(v.begin(), v.end(), kv.second.get()) == v.end()) v.push_back(kv.second.get());
+  return v;
 }
 
 size_t grid_tiles(const b200nav_grid* g) {
@@ -219,6 +236,62 @@ int fill_nan(b200nav_grid* g, float* p, size_t n) {
   const size_t blocks = std::min<size_t>((n + threads - 1) / threads, (size_t)g->ctx->sm_count * 16);
   grid_fill_kernel<<<(unsigned)std::max<size_t>(blocks, 1), threads, 0, g->ctx->stream>>>(p, n, nanf(""));
   return check_launch(g->ctx, "grid_fill_kernel");
+}
+
+size_t coded_robot_bytes(const b200nav_grid* g) { return grid_tiles(g) * (size_t)HIMM_TILE_BYTES; }
+int grid_tiles_r(const b200nav_grid* g) { return (g->dims.rows + HIMM_TILE - 1) / HIMM_TILE; }
+
+LayerRef layer_ref(const b200nav_grid* g, const Layer* l, int robot) {
+  LayerRef r;
+  r.coded = l->coded ? 1 : 0;
+  r.rows = g->dims.rows;
+  r.tiles_r = grid_tiles_r(g);
+  r.base = l->coded ? static_cast<const void*>(l->cdev() + coded_robot_bytes(g) * robot)
+                    : static_cast<const void*>(l->fdev() + (size_t)g->dims.rows * g->dims.cols * robot);
+  return r;
+}
+
+unsigned conv_blocks(const b200nav_grid* g, size_t n, int threads) {
+  return (unsigned)std::max<size_t>(1, std::min<size_t>((n + threads - 1) / threads, (size_t)g->ctx->sm_count * 16));
+}
+
+/* every cell of every robot := NaN */
+int fill_layer_nan(b200nav_grid* g, Layer* l) {
+  if (!l->coded) return fill_nan(g, l->fdev(), g->layer_elems());
+  const size_t recs = grid_tiles(g) * (size_t)g->n_robots;
+  coded_fill_kernel<<<conv_blocks(g, recs * HIMM_TILE_BYTES, 256), 256, 0, g->ctx->stream>>>(
+      l->cdev(), recs, g->dims.rows, g->dims.cols, grid_tiles_r(g), (int)grid_tiles(g));
+  return check_launch(g->ctx, "coded_fill_kernel");
+}
+
+/* CODED -> FLOAT, for good (foreign values arrived or the host wants the raw float pointer) */
+int layer_to_float(b200nav_grid* g, Layer* l) {
+  if (!l->coded) return B200NAV_OK;
+  b200nav_ctx* ctx = g->ctx;
+  float* f = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void**)&f, g->layer_elems() * sizeof(float)));
+  coded_to_float_kernel<<<conv_blocks(g, g->layer_elems(), 256), 256, 0, ctx->stream>>>(
+      l->cdev(), f, g->dims.rows, g->dims.cols, grid_tiles_r(g), coded_robot_bytes(g), g->layer_elems());
+  int rc = check_launch(ctx, "coded_to_float_kernel");
+  if (rc == B200NAV_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = B200NAV_ECUDA;
+  if (rc) {
+    cudaFree(f);
+    return rc;
+  }
+  cudaFree(l->dev);
+  l->dev = f;
+  l->coded = false;
+  return reset_free_cols(g, l, -1);
+}
+
+int alloc_layer(b200nav_grid* g, Layer* l, bool coded) {
+  l->coded = coded;
+  const size_t bytes = coded ? coded_robot_bytes(g) * g->n_robots : g->layer_elems() * sizeof(float);
+  CUDA_TRY(g->ctx, cudaMalloc(&l->dev, bytes));
+  const size_t fc_bytes = sizeof(unsigned long long) * grid_tiles(g) * g->n_robots;
+  CUDA_TRY(g->ctx, cudaMalloc((void**)&l->free_cols, fc_bytes));
+  CUDA_TRY(g->ctx, cudaMemsetAsync(l->free_cols, 0, fc_bytes, g->ctx->stream));
+  return B200NAV_OK;
 }
 
 int upload_geom(b200nav_grid* g) {
@@ -271,6 +344,7 @@ int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, c
   a.dims = g->dims;
   a.geom = g->geom_dev;
   a.layer = lay->dev;
+  a.coded = lay->coded ? 1 : 0;
   a.free_cols = lay->free_cols + grid_tiles(g) * (size_t)robot0;
   a.samples = dev_samples;
   a.origins = cloud.origins;
@@ -326,15 +400,15 @@ int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int 
 
 int himm_launch_tile(b200nav_grid* g, const HimmArgs& a) {
   b200nav_ctx* ctx = g->ctx;
-  auto kern = himm_tile_kernel<kSub, kListCap>;
   /* persistent: as many one-warp CTAs as can be resident (32 per SM), never more than there are tiles */
   dim3 grid((unsigned)std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * 32));
   {
     ProfScope ps(ctx, PROF_HIMM_TILE);
     const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
-    kern<<<grid, TileCfg::kThreads, smem, ctx->stream>>>(a);
+    if (a.coded) himm_tile_coded_kernel<kListCap><<<grid, TileCfg::kThreads, smem, ctx->stream>>>(a);
+    else himm_tile_kernel<kSub, kListCap><<<grid, TileCfg::kThreads, smem, ctx->stream>>>(a);
   }
-  return check_launch(ctx, "himm_tile_kernel");
+  return check_launch(ctx, a.coded ? "himm_tile_coded_kernel" : "himm_tile_kernel");
 }
 
 int himm_launch(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
@@ -439,7 +513,7 @@ size_t vfh_smem_bytes(const b200nav_vfh* v, bool from_grid, int box_r, int box_c
   return b;
 }
 
-int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const float* layer, const b200nav_vfh_input* dev_in,
+int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const Layer* layer, const b200nav_vfh_input* dev_in,
                const double* dev_ranges, b200nav_command* dev_out, int robot0, int n) {
   b200nav_ctx* ctx = v->ctx;
   VfhGridArgs ga;
@@ -452,10 +526,14 @@ int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const float* layer, const b200na
     vfh_window_box(v, g, box_r, box_c);
     ga.dims = g->dims;
     ga.geom = g->geom_dev;
-    ga.layer = layer;
+    ga.layer = layer->dev;
+    ga.coded = layer->coded ? 1 : 0;
+    ga.tiles_r = grid_tiles_r(g);
+    ga.tiles_c = (g->dims.cols + HIMM_TILE - 1) / HIMM_TILE;
     ga.box_r = box_r;
     ga.box_c = box_c;
-    ga.use_tma = vfh_prepare_tmap(v, g, layer, box_r, box_c) ? 1 : 0;
+    /* the tiled TMA window load works on the FLOAT layout; CODED layers are read through cells.cuh */
+    ga.use_tma = (!layer->coded && vfh_prepare_tmap(v, g, layer->fdev(), box_r, box_c)) ? 1 : 0;
     if (ga.use_tma) tm = v->tmap;
     smem = vfh_smem_bytes(v, true, box_r, box_c);
     if (smem > (size_t)kVfhMaxSmem) return set_err(ctx, B200NAV_ERANGE, "VFH window too large for shared memory (%zu B)", smem);
@@ -474,6 +552,8 @@ int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const float* layer, const b200na
 /* Opt in to > 48 KB dynamic shared memory once per device (attributes are per device). */
 int configure_kernels(b200nav_ctx* ctx) {
   CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_kernel<kSub, kListCap>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_coded_kernel<kListCap>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
   CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
   CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
@@ -626,11 +706,9 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   if (!g) return B200NAV_OK;
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
-  for (auto& kv : g->layers)
-    if (kv.second.owned && kv.second.dev) {
-      cudaFree(kv.second.dev);
-      cudaFree(kv.second.free_cols);
-    }
+  g->layers.clear(); /* frees the device buffers */
+  g->stage.release();
+  g->convflag.release();
   if (g->geom_dev) cudaFree(g->geom_dev);
   g->samples.release();
   g->segs.release();
@@ -660,16 +738,12 @@ int b200nav_grid_add_layer(b200nav_grid* g, const char* name) {
   if (!g || !name || !*name) return B200NAV_EINVAL;
   if (find_layer(g, name)) return B200NAV_OK; /* map_.exists(typeName) (map_updater.h:12) */
   CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
-  Layer l;
-  CUDA_TRY(g->ctx, cudaMalloc((void**)&l.dev, g->layer_elems() * sizeof(float)));
-  int rc = fill_nan(g, l.dev, g->layer_elems());
-  if (rc) {
-    cudaFree(l.dev);
-    return rc;
-  }
-  const size_t fc_bytes = sizeof(unsigned long long) * grid_tiles(g) * g->n_robots;
-  CUDA_TRY(g->ctx, cudaMalloc((void**)&l.free_cols, fc_bytes));
-  CUDA_TRY(g->ctx, cudaMemsetAsync(l.free_cols, 0, fc_bytes, g->ctx->stream));
+  static const bool float_layers = getenv("B200NAV_FLOAT_LAYERS") != nullptr; /* testing aid: start in FLOAT format */
+  auto l = std::make_shared<Layer>();
+  int rc = alloc_layer(g, l.get(), !float_layers);
+  if (rc) return rc;
+  rc = fill_layer_nan(g, l.get());
+  if (rc) return rc;
   g->layers[name] = l;
   return B200NAV_OK;
 }
@@ -678,17 +752,9 @@ int b200nav_grid_alias_layer(b200nav_grid* g, const char* alias, const char* tar
   if (!g || !alias || !target) return B200NAV_EINVAL;
   Layer* t = find_layer(g, target);
   if (!t) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", target);
-  Layer* a = find_layer(g, alias);
-  if (a && a->owned && a->dev && a->dev != t->dev) {
-    cudaStreamSynchronize(g->ctx->stream);
-    cudaFree(a->dev);
-    cudaFree(a->free_cols);
-  }
-  Layer l;
-  l.dev = t->dev;
-  l.free_cols = t->free_cols;
-  l.owned = false;
-  g->layers[alias] = l;
+  if (find_layer(g, alias) == t) return B200NAV_OK;
+  cudaStreamSynchronize(g->ctx->stream); /* a layer replaced by the alias may still be in use */
+  g->layers[alias] = g->layers[target];
   return B200NAV_OK;
 }
 
@@ -696,9 +762,18 @@ int b200nav_grid_copy_layer(b200nav_grid* g, const char* dst, const char* src) {
   if (!g) return B200NAV_EINVAL;
   Layer *d = find_layer(g, dst), *s = find_layer(g, src);
   if (!d || !s) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", !d ? dst : src);
-  if (d->dev == s->dev) return B200NAV_OK;
-  CUDA_TRY(g->ctx, cudaMemcpyAsync(d->dev, s->dev, g->layer_elems() * sizeof(float), cudaMemcpyDeviceToDevice,
-                                   g->ctx->stream));
+  if (d == s) return B200NAV_OK;
+  if (d->coded != s->coded) { /* the destination takes the source's format */
+    CUDA_TRY(g->ctx, cudaStreamSynchronize(g->ctx->stream));
+    void* nd = nullptr;
+    const size_t nbytes = s->coded ? coded_robot_bytes(g) * g->n_robots : g->layer_elems() * sizeof(float);
+    CUDA_TRY(g->ctx, cudaMalloc(&nd, nbytes));
+    cudaFree(d->dev);
+    d->dev = nd;
+    d->coded = s->coded;
+  }
+  const size_t bytes = s->coded ? coded_robot_bytes(g) * g->n_robots : g->layer_elems() * sizeof(float);
+  CUDA_TRY(g->ctx, cudaMemcpyAsync(d->dev, s->dev, bytes, cudaMemcpyDeviceToDevice, g->ctx->stream));
   /* the copy carries the source's free-column knowledge along */
   CUDA_TRY(g->ctx, cudaMemcpyAsync(d->free_cols, s->free_cols, sizeof(unsigned long long) * grid_tiles(g) * g->n_robots,
                                    cudaMemcpyDeviceToDevice, g->ctx->stream));
@@ -712,15 +787,14 @@ int b200nav_grid_clear(b200nav_grid* g, const char* layer) {
     if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer);
     int rc = reset_free_cols(g, l, -1);
     if (rc) return rc;
-    return fill_nan(g, l->dev, g->layer_elems());
+    return fill_layer_nan(g, l);
   }
-  for (auto& kv : g->layers)
-    if (kv.second.owned) {
-      int rc = reset_free_cols(g, &kv.second, -1);
-      if (rc) return rc;
-      rc = fill_nan(g, kv.second.dev, g->layer_elems());
-      if (rc) return rc;
-    }
+  for (Layer* l : unique_layers(g)) {
+    int rc = reset_free_cols(g, l, -1);
+    if (rc) return rc;
+    rc = fill_layer_nan(g, l);
+    if (rc) return rc;
+  }
   return B200NAV_OK;
 }
 
@@ -729,11 +803,40 @@ int b200nav_grid_upload(b200nav_grid* g, int robot, const char* layer, const flo
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   const size_t n = (size_t)g->dims.rows * g->dims.cols;
+  b200nav_ctx* ctx = g->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   int rrc = reset_free_cols(g, l, robot);
   if (rrc) return rrc;
-  CUDA_TRY(g->ctx, cudaMemcpyAsync(l->dev + n * robot, colmajor, n * sizeof(float), cudaMemcpyHostToDevice,
-                                   g->ctx->stream));
-  return sync_stream(g->ctx);
+  if (l->coded) {
+    /* float staging -> check that every value has a code -> encode into the robot's records */
+    CUDA_TRY(ctx, g->stage.reserve(n * sizeof(float)));
+    CUDA_TRY(ctx, g->convflag.reserve(sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(g->convflag.p, 0, sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g->stage.p, colmajor, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* dst = l->cdev() + coded_robot_bytes(g) * robot;
+    for (int pass = 0; pass < 2; pass++) {
+      coded_from_float_kernel<<<conv_blocks(g, n, 256), 256, 0, ctx->stream>>>(
+          static_cast<const float*>(g->stage.p), dst, g->dims.rows, g->dims.cols, grid_tiles_r(g), coded_robot_bytes(g),
+          n, pass == 0 ? 1 : 0, static_cast<int*>(g->convflag.p));
+      int rc = check_launch(ctx, "coded_from_float_kernel");
+      if (rc) return rc;
+      if (pass == 0) {
+        int bad = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&bad, g->convflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (bad) { /* values outside the HIMM set: the layer leaves the coded format */
+          rc = layer_to_float(g, l);
+          if (rc) return rc;
+          CUDA_TRY(ctx, cudaMemcpyAsync(l->fdev() + n * robot, g->stage.p, n * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+          break;
+        }
+      }
+    }
+    return sync_stream(ctx);
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(l->fdev() + n * robot, colmajor, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  return sync_stream(ctx);
 }
 
 int b200nav_grid_download(b200nav_grid* g, int robot, const char* layer, float* colmajor) {
@@ -741,9 +844,20 @@ int b200nav_grid_download(b200nav_grid* g, int robot, const char* layer, float* 
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   const size_t n = (size_t)g->dims.rows * g->dims.cols;
-  CUDA_TRY(g->ctx, cudaMemcpyAsync(colmajor, l->dev + n * robot, n * sizeof(float), cudaMemcpyDeviceToHost,
-                                   g->ctx->stream));
-  return sync_stream(g->ctx);
+  b200nav_ctx* ctx = g->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const float* src = l->coded ? nullptr : l->fdev() + n * robot;
+  if (l->coded) {
+    CUDA_TRY(ctx, g->stage.reserve(n * sizeof(float)));
+    coded_to_float_kernel<<<conv_blocks(g, n, 256), 256, 0, ctx->stream>>>(
+        l->cdev() + coded_robot_bytes(g) * robot, static_cast<float*>(g->stage.p), g->dims.rows, g->dims.cols,
+        grid_tiles_r(g), coded_robot_bytes(g), n);
+    int rc = check_launch(ctx, "coded_to_float_kernel");
+    if (rc) return rc;
+    src = static_cast<const float*>(g->stage.p);
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(colmajor, src, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_stream(ctx);
 }
 
 int b200nav_grid_set_geometry(b200nav_grid* g, int robot, double pos_x, double pos_y, int start0, int start1) {
@@ -786,15 +900,18 @@ int b200nav_grid_move(b200nav_grid* g, int robot, double x, double y, int* moved
   const size_t per_robot = (size_t)g->dims.rows * g->dims.cols;
   auto clear_strip = [&](int axis, int index, int n) -> int {
     if (n <= 0) return B200NAV_OK;
-    for (auto& kv : g->layers) {
-      if (!kv.second.owned) continue;
-      int rrc = reset_free_cols(g, &kv.second, robot);
+    for (Layer* l : unique_layers(g)) {
+      int rrc = reset_free_cols(g, l, robot);
       if (rrc) return rrc;
-      float* base = kv.second.dev + per_robot * robot;
       const int r0 = axis == 0 ? index : 0, nr = axis == 0 ? n : g->dims.rows;
       const int c0 = axis == 1 ? index : 0, nc = axis == 1 ? n : g->dims.cols;
       dim3 grid((unsigned)((nr + 127) / 128), (unsigned)std::min(nc, 65535));
-      grid_fill_rect_kernel<<<grid, 128, 0, g->ctx->stream>>>(base, g->dims.rows, r0, nr, c0, nc, nanf(""));
+      if (l->coded)
+        coded_fill_rect_kernel<<<grid, 128, 0, g->ctx->stream>>>(l->cdev() + coded_robot_bytes(g) * robot,
+                                                                 grid_tiles_r(g), r0, nr, c0, nc, HIMM_CODE_NAN);
+      else
+        grid_fill_rect_kernel<<<grid, 128, 0, g->ctx->stream>>>(l->fdev() + per_robot * robot, g->dims.rows, r0, nr,
+                                                                c0, nc, nanf(""));
       int rc = check_launch(g->ctx, "grid_fill_rect_kernel");
       if (rc) return rc;
     }
@@ -846,7 +963,7 @@ int b200nav_grid_to_occupancy(b200nav_grid* g, int robot, const char* layer, flo
   const RobotGeom& rg = g->geom_host[robot];
   const int threads = 256;
   grid_to_occupancy_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, g->ctx->stream>>>(
-      l->dev + n * robot, g->dims.rows, g->dims.cols, rg.start0, rg.start1, data_min, data_max,
+      layer_ref(g, l, robot), g->dims.rows, g->dims.cols, rg.start0, rg.start1, data_min, data_max,
       static_cast<int8_t*>(g->occ.p));
   int rc = check_launch(g->ctx, "grid_to_occupancy_kernel");
   if (rc) return rc;
@@ -866,9 +983,8 @@ int b200nav_grid_query_blocked(b200nav_grid* g, int robot, const char* layer, co
   CUDA_TRY(ctx, g->samples.reserve(sizeof(double) * 2 * (size_t)n));
   CUDA_TRY(ctx, g->occ.reserve((size_t)n));
   CUDA_TRY(ctx, cudaMemcpyAsync(g->samples.p, host_xy, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  const size_t per = (size_t)g->dims.rows * g->dims.cols;
   grid_blocked_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->stream>>>(
-      g->dims, g->geom_host[robot], l->dev + per * robot, static_cast<const double*>(g->samples.p), n, radius,
+      g->dims, g->geom_host[robot], layer_ref(g, l, robot), static_cast<const double*>(g->samples.p), n, radius,
       static_cast<uint8_t*>(g->occ.p));
   int rc = check_launch(ctx, "grid_blocked_kernel");
   if (rc) return rc;
@@ -886,7 +1002,22 @@ int b200nav_grid_layer_written(b200nav_grid* g, const char* layer, int robot) {
 void* b200nav_grid_layer_devptr(b200nav_grid* g, const char* layer) {
   if (!g) return nullptr;
   Layer* l = find_layer(g, layer);
-  return l ? l->dev : nullptr;
+  if (!l) return nullptr;
+  /* the raw pointer is the reference's float layout: a CODED layer is converted (and stays FLOAT) */
+  if (l->coded && layer_to_float(g, l) != B200NAV_OK) return nullptr;
+  return l->dev;
+}
+
+int b200nav_grid_has_layer(const b200nav_grid* g, const char* layer) {
+  if (!g || !layer) return 0;
+  return g->layers.find(layer) != g->layers.end() ? 1 : 0;
+}
+
+int b200nav_grid_layer_format(b200nav_grid* g, const char* layer) {
+  if (!g) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  return l->coded ? B200NAV_LAYER_CODED : B200NAV_LAYER_FLOAT;
 }
 
 /* ================================================================================================================
@@ -1212,13 +1343,13 @@ int b200nav_vfh_get_max_turnrate(const b200nav_vfh* v, int speed) {
 static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int robot0, int n,
                         const b200nav_vfh_input* host_in, const double* host_ranges, b200nav_command* host_out) {
   b200nav_ctx* ctx = v->ctx;
-  const float* lay = nullptr;
+  const Layer* lay = nullptr;
   if (g) {
     if (g->ctx != ctx) return set_err(ctx, B200NAV_EINVAL, "grid and vfh belong to different contexts");
     if (robot0 + n > g->n_robots) return set_err(ctx, B200NAV_EINVAL, "robot index beyond the grid's robots");
     Layer* l = find_layer(g, layer);
     if (!l) return set_err(ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
-    lay = l->dev;
+    lay = l;
   }
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, v->in_buf.reserve(sizeof(b200nav_vfh_input) * (size_t)n));
@@ -1266,7 +1397,7 @@ int b200nav_vfh_update_batched_dev(b200nav_vfh* v, b200nav_grid* g, const char* 
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(v->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   CUDA_TRY(v->ctx, cudaSetDevice(v->ctx->device));
-  return vfh_launch(v, g, l->dev, dev_in, nullptr, dev_out, 0, v->n_robots);
+  return vfh_launch(v, g, l, dev_in, nullptr, dev_out, 0, v->n_robots);
 }
 
 int b200nav_vfh_read_state(b200nav_vfh* v, int robot, float* origin_hist, float* hist, float* last_binary,

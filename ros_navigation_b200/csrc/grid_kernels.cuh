@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "cells.cuh"
 #include "geometry.h"
 
 namespace b200nav {
@@ -28,13 +29,13 @@ __global__ void grid_fill_rect_kernel(float* __restrict__ base, int rows, int r0
 }
 
 /* One thread per buffer cell: value -> int8 [-1, 0..100] written at the reversed unwrapped linear index. */
-__global__ void grid_to_occupancy_kernel(const float* __restrict__ layer, int rows, int cols, int start0, int start1,
+__global__ void grid_to_occupancy_kernel(const LayerRef layer, int rows, int cols, int start0, int start1,
                                          float data_min, float data_max, int8_t* __restrict__ out) {
   const size_t n = (size_t)rows * cols;
   const size_t lin = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lin >= n) return;
   const int b0 = (int)(lin % rows), b1 = (int)(lin / rows);
-  float value = (layer[lin] - data_min) / (data_max - data_min);
+  float value = (layer.at(b0, b1) - data_min) / (data_max - data_min);
   if (isnan(value) || (value < 0))
     value = -1;
   else
@@ -51,7 +52,7 @@ __global__ void grid_to_occupancy_kernel(const float* __restrict__ layer, int ro
  * stride over the cells of the circle's bounding block; out[q] = 1 if any cell centre within `radius` holds a
  * non-NaN value > 0.  Lets the host-side RRT planner test candidates against the device-resident master layer
  * without downloading it (rrt_planner.cpp:53). */
-__global__ void grid_blocked_kernel(GridDims d, RobotGeom g, const float* __restrict__ layer,
+__global__ void grid_blocked_kernel(GridDims d, RobotGeom g, const LayerRef layer,
                                     const double* __restrict__ xy, int n, double radius, uint8_t* __restrict__ out) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= n) return;
@@ -87,7 +88,7 @@ __global__ void grid_blocked_kernel(GridDims d, RobotGeom g, const float* __rest
       position_from_index(b0, b1, d.len_x, d.len_y, g.pos_x, g.pos_y, d.res, d.rows, d.cols, g.start0, g.start1, px, py);
       const double dx = px - x, dy = py - y;
       if (!(dx * dx + dy * dy <= r2)) continue;
-      const float v = layer[(size_t)b1 * d.rows + b0];
+      const float v = layer.at(b0, b1);
       if (v > 0.0f) hit = true; /* false for NaN */
     }
   }

@@ -25,18 +25,19 @@
 #include <stdint.h>
 
 #include "../../include/b200nav.h"
+#include "cells.cuh"
 #include "geometry.h"
 
 namespace b200nav {
 
-#define HIMM_TILE 64        /* tile edge in cells (one warp owns one tile)                                  */
 #define HIMM_CHUNK 2048     /* max beams per chunk: a tile's beam set is a bit mask of <= 2048 bits          */
 #define HIMM_MASK_WORDS (HIMM_CHUNK / 32)
 
 struct HimmArgs {
   GridDims dims;
   const RobotGeom* geom;          /* [n_robots]                                   */
-  float* layer;                   /* [n_robots][cols][rows]                       */
+  int coded;                      /* layer format (cells.cuh)                      */
+  void* layer;                    /* FLOAT: float [n_robots][cols][rows]; CODED: bytes [n_robots][tiles][4352] (cells.cuh) */
   const b200nav_sample* samples;  /* device; NULL when the cloud form below is used */
   const double* origins;          /* cloud form: [n_active][2] laser origin per robot  */
   const float2* xy;               /* cloud form: [total] float32 end points            */
@@ -285,26 +286,6 @@ struct HimmTileCfg {
   static constexpr size_t kSmemBytes = kTileBytes + sizeof(uint16_t) * LIST_CAP;
   static_assert(SUB == 64, "tile edge is 64 (two rows per lane, 64-bit column masks)");
 };
-
-/* Codes: 0 = NaN (unknown), k = value/10 + 1 for value in {0,10,...,180} (1..19).  With this numbering
- *   clearCell(c) = max(c - 1, 1)                              (NaN -> 0; 0 stays 0)
- *   markCell(c)  = c <= 1 ? 4 : (c <= 16 ? c + 3 : c)         (NaN or 0 -> 30; <= 150 -> +30) */
-#define HIMM_CODE_NAN 0
-
-/* Small non-negative integers <-> float without I2F/F2I: float(0x4B000000 + k) == 8388608 + k exactly. */
-__device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B000000 + k) - 8388608.0f; }
-
-/* float -> code; returns 255 for a value outside the HIMM set */
-__device__ __forceinline__ unsigned himm_encode(float v) {
-  /* c = round(v/10) through the magic add; garbage for NaN / negative / huge inputs is rejected by the checks */
-  const int c = __float_as_int(v * 0.1f + 8388608.0f) - 0x4B000000;
-  const bool in_set = (unsigned)c <= 18u && small_int_to_float(c * 10) == v && __float_as_uint(v) != 0x80000000u;
-  /* -0.0f compares equal to 0 but has another bit pattern: it stays out of the set so that it round-trips */
-  return (v != v) ? (unsigned)HIMM_CODE_NAN : (in_set ? (unsigned)(c + 1) : 255u);
-}
-__device__ __forceinline__ float himm_decode(unsigned c) {
-  return c == HIMM_CODE_NAN ? __int_as_float(0x7fc00000) : small_int_to_float((int)(c * 10u) - 10);
-}
 
 /* Tile views: the walk is written once against this interface.
  *   sensitive(off)   does the result of visiting this cell depend on how many beams visit it / in which order?
@@ -570,7 +551,7 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
   if (a.single_n >= 0) beg = 0;
   else beg = __ldg(&a.offsets[rel]);
 
-  float* gbase = a.layer + (size_t)robot * rows * cols;
+  float* gbase = static_cast<float*>(a.layer) + (size_t)robot * rows * cols;
   float* gtile = gbase + (size_t)C0 * rows + R0;
   unsigned long long loaded = 0ull; /* columns staged in shared memory (bit c = column C0+c) */
   bool foreign = false;             /* tile holds values outside the HIMM set -> float view on global memory */
@@ -806,6 +787,172 @@ __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
 
   /* the last warp to finish re-arms the counters for the next update */
   if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(&a.counters[2], 1) == (int)gridDim.x - 1) {
+      a.counters[0] = 0;
+      a.counters[1] = 0;
+      a.counters[2] = 0;
+      a.counters[3] = 0;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K1 for CODED layers (cells.cuh): the tile record in HBM is the shared-memory image, so a work item is
+ *   one bulk async copy in (cp.async.bulk global -> shared, completion on an mbarrier), the in-order walk, one bulk
+ *   async copy out (shared -> global).  No conversion, no per-column address arithmetic, 4352 bytes each way.
+ * Free-tile shortcut: a record whose cells are all 0 (code 1) is remembered in free_cols[] (all ones); while that
+ * holds, a beam set without marks cannot change the tile and the work item is dropped before any copy.
+ * ------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int LIST_CAP>
+__global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
+  static_assert(LIST_CAP == HIMM_CHUNK, "chunk constant");
+  extern __shared__ __align__(128) unsigned char himm_smem_raw[];
+  uint8_t* tile = himm_smem_raw;
+  uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + HIMM_TILE_BYTES); /* a.chunk_beams entries */
+  __shared__ __align__(8) unsigned long long s_mbar;
+
+  uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
+  asm volatile("mov.u32 %0, %0;" : "+r"(tile_saddr));
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+
+  const int lane = threadIdx.x;
+  const int rows = a.dims.rows, cols = a.dims.cols;
+  const int n_tiles = a.tiles_r * a.tiles_c;
+  const int n_heavy = *reinterpret_cast<volatile int*>(&a.counters[0]); /* final: the prep kernel has completed */
+  const int n_work = n_heavy + *reinterpret_cast<volatile int*>(&a.counters[3]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase = 0; /* mbarrier phase parity of the next copy-in */
+
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(&a.counters[1], 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= n_work) break;
+    const int rt = a.worklist[w < n_heavy ? w : a.worklist_cap - 1 - (w - n_heavy)];
+    const int rel = rt / n_tiles, tile_id = rt - rel * n_tiles;
+    const int robot = a.robot0 + rel;
+    const int tile_r = tile_id % a.tiles_r, tile_c = tile_id / a.tiles_r;
+    const int R0 = tile_r * HIMM_TILE, C0 = tile_c * HIMM_TILE;
+    const int R1 = min(R0 + HIMM_TILE, rows) - 1, C1 = min(C0 + HIMM_TILE, cols) - 1;
+    int beg;
+    if (a.single_n >= 0) beg = 0;
+    else beg = __ldg(&a.offsets[rel]);
+    uint8_t* grec = static_cast<uint8_t*>(a.layer) + ((size_t)robot * n_tiles + tile_id) * HIMM_TILE_BYTES;
+    if (lane == 0) a.touched[rt] = 0u;
+    const bool known_free = a.free_cols[rt] == ~0ull; /* warp-uniform load */
+    bool staged = false; /* copy-in issued */
+    bool ready = false;  /* copy-in complete (waited for) */
+
+    auto stage = [&]() {
+      if (lane == 0) {
+        /* the previous work item's store must have finished READING the buffer before it is overwritten */
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "n"(HIMM_TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tile_saddr), "l"(grec), "n"(HIMM_TILE_BYTES), "r"(mbar)
+                     : "memory");
+      }
+      staged = true;
+    };
+    if (!known_free) stage(); /* the copy flies while the beam list is being built */
+
+    for (int chunk = 0; chunk < a.n_chunks; chunk++) {
+      const size_t t = ((size_t)rel * a.n_chunks + chunk) * (size_t)n_tiles + tile_id;
+      /* ---- this tile's beam set: bit mask written by the prep kernel; consume and clear it ---- */
+      uint32_t* mw = a.beam_masks + t * a.mask_words;
+      const uint32_t w0 = (lane < a.mask_words) ? mw[lane] : 0u, w1 = (lane + 32 < a.mask_words) ? mw[lane + 32] : 0u;
+      if (__ballot_sync(0xffffffffu, (w0 | w1) != 0u) == 0u) continue;
+      if (w0) mw[lane] = 0u;
+      if (w1) mw[lane + 32] = 0u;
+      /* expand the mask into the ordered beam list: lane L owns words L and L+32 */
+      const int p0 = __popc(w0), p1 = __popc(w1);
+      int inc0 = p0, inc1 = p1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u0 = __shfl_up_sync(0xffffffffu, inc0, o), u1 = __shfl_up_sync(0xffffffffu, inc1, o);
+        if (lane >= o) {
+          inc0 += u0;
+          inc1 += u1;
+        }
+      }
+      const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+      const int n_list = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
+      {
+        int pos = inc0 - p0;
+        for (uint32_t ww = w0; ww; ww &= ww - 1) list[pos++] = (uint16_t)(32 * lane + __ffs(ww) - 1);
+        pos = tot0 + inc1 - p1;
+        for (uint32_t ww = w1; ww; ww &= ww - 1) list[pos++] = (uint16_t)(32 * (lane + 32) + __ffs(ww) - 1);
+      }
+      __syncwarp();
+      const BeamSeg* segs = a.segs + beg + chunk * a.chunk_beams;
+
+      if (!staged) {
+        /* ---- free-space shortcut: every cell is 0 and no beam of this chunk marks -> nothing can change ---- */
+        bool any_mark = false;
+        for (int j = lane; j < n_list; j += 32) {
+          const BeamSeg b = segs[list[j]];
+          any_mark |= b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1;
+        }
+        if (!__any_sync(0xffffffffu, any_mark)) {
+          if (lane == 0) atomicAdd(&a.counters[4], 1); /* statistics: tiles skipped */
+          continue;
+        }
+        stage();
+      }
+      if (lane == 0) atomicAdd(&a.counters[5], 1); /* statistics: tiles processed */
+      if (!ready) { /* the first chunk that needs the data waits for the copy */
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+        ready = true;
+      }
+      himm_apply_list(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane);
+      __syncwarp(); /* the list is rewritten by the next chunk */
+    }
+
+    if (staged) {
+      if (!ready) { /* staged but no chunk had beams (stale work item): keep the barrier phase right */
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+      }
+      /* is the whole record free now?  (pad bytes and cells outside the grid hold the free code for good) */
+      unsigned diff = 0;
+      for (int i = lane; i < HIMM_TILE_BYTES / 16; i += 32) {
+        uint32_t x, y, z, q;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(q) : "r"(tile_saddr + 16 * i) : "memory");
+        diff |= (x ^ 0x01010101u) | (y ^ 0x01010101u) | (z ^ 0x01010101u) | (q ^ 0x01010101u);
+      }
+      const bool all_free = !__any_sync(0xffffffffu, diff != 0u);
+      /* generic-proxy writes of the walk -> visible to the async proxy, then one lane sends the record home */
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grec), "r"(tile_saddr), "n"(HIMM_TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (all_free != known_free) a.free_cols[rt] = all_free ? ~0ull : 0ull;
+      }
+    }
+    __syncwarp();
+  } /* persistent loop */
+
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* all records are home before the CTA retires */
+    /* the last warp to finish re-arms the counters for the next update */
     __threadfence();
     if (atomicAdd(&a.counters[2], 1) == (int)gridDim.x - 1) {
       a.counters[0] = 0;

@@ -27,6 +27,7 @@
 #include <stdint.h>
 
 #include "../../include/b200nav.h"
+#include "cells.cuh"
 #include "geometry.h"
 #include "vfh_tables.h"
 
@@ -58,7 +59,9 @@ struct VfhDev {
 struct VfhGridArgs {
   GridDims dims;
   const RobotGeom* geom;
-  const float* layer;
+  const void* layer; /* FLOAT: float [n_robots][cols][rows]; CODED: bytes [n_robots][tiles][4352] (cells.cuh) */
+  int coded;
+  int tiles_r, tiles_c;
   int box_r, box_c; /* TMA box (floats) = smem window pitch / columns */
   int use_tma;
 };
@@ -178,7 +181,14 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
               : "memory");
         }
       }
-      const float* lay = ga.layer + (size_t)robot * ga.dims.rows * ga.dims.cols;
+      LayerRef lay;
+      lay.coded = ga.coded;
+      lay.rows = ga.dims.rows;
+      lay.tiles_r = ga.tiles_r;
+      lay.base = ga.coded ? static_cast<const void*>(static_cast<const uint8_t*>(ga.layer) +
+                                                     (size_t)robot * ga.tiles_r * ga.tiles_c * HIMM_TILE_BYTES)
+                          : static_cast<const void*>(static_cast<const float*>(ga.layer) +
+                                                     (size_t)robot * ga.dims.rows * ga.dims.cols);
       const int ncell = si.size_r * si.size_c;
       const double res = ga.dims.res;
       const double offx = si.pos_x + (0.5 * si.len_x - 0.5 * res), offy = si.pos_y + (0.5 * si.len_y - 0.5 * res);
@@ -195,7 +205,7 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
             wrap_index(b0, ga.dims.rows);
             wrap_index(b1, ga.dims.cols);
           }
-          value = lay[(size_t)b1 * ga.dims.rows + b0];
+          value = lay.at(b0, b1);
         }
         if (isnan(value) || value <= c.occupied_threshold) continue;
         const double px = offx + res * int_to_f64(-i0), py = offy + res * int_to_f64(-i1);

@@ -86,6 +86,13 @@ class DeviceGridMap:
     def layer_written(self, layer, robot=-1):
         check(lib().b200nav_grid_layer_written(self.h, layer.encode(), int(robot)), self.ctx.h)
 
+    def layer_format(self, layer):
+        """"coded" (one byte per cell, the default) or "float" (the reference's float matrix)."""
+        rc = lib().b200nav_grid_layer_format(self.h, layer.encode())
+        if rc < 0:
+            check(rc, self.ctx.h)
+        return "coded" if rc == 1 else "float"
+
     def layer_devptr(self, layer):
         return lib().b200nav_grid_layer_devptr(self.h, layer.encode())
 

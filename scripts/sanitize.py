@@ -27,4 +27,23 @@ for it in range(3):
     v.update_batched(dg, "master", inp)
 for r in range(2):
     assert_layers_equal(dg.download("laser", robot=r), lay[r], "robot %d" % r)
+assert dg.layer_format("laser") == "float"
+
+# the same on byte-coded layers (no foreign values): bulk-copy staged tile kernel, coded readers, move
+cg = DeviceGridMap(ctx, (10.0, 6.5), 0.05, n_robots=2, layers=("laser",))
+cg.alias("master", "laser")
+clay = [O.new_layer(g), O.new_layer(g)]
+cgeo = [O.make_geom(10.0, 6.5, 0.05), O.make_geom(10.0, 6.5, 0.05)]
+for it in range(3):
+    per = [lidar_samples(rng, g, (0.3, 0.1), 700, 0.2, 4.0, clear_frac=0.1), random_samples(rng, g, 300)]
+    off = np.array([0, len(per[0]), len(per[0]) + len(per[1])], np.int32)
+    cg.himm_update_batched("laser", np.concatenate(per), off)
+    for r in range(2):
+        O.himm_update(cgeo[r], clay[r], per[r])
+    v.update_batched(cg, "master", inp)
+    cg.move((0.4 * (it + 1), -0.2), robot=0)
+    O.move(cgeo[0], [clay[0]], 0.4 * (it + 1), -0.2)
+for r in range(2):
+    assert_layers_equal(cg.download("laser", robot=r), clay[r], "coded robot %d" % r)
+assert cg.layer_format("laser") == "coded"
 print("sanitize workload OK")
