@@ -54,6 +54,11 @@ typedef struct b200nav_vfh b200nav_vfh;
 int b200nav_ctx_create(int device, void* cuda_stream, b200nav_ctx** out);
 int b200nav_ctx_destroy(b200nav_ctx* ctx);
 int b200nav_ctx_synchronize(b200nav_ctx* ctx);
+/* Pipelining aid for the *_async entry points: fence() marks the current end of the context's stream and returns a
+ * ticket; wait() blocks the calling thread until everything enqueued before that fence has completed (tickets may be
+ * waited for in any order; only the 8 most recent fences are distinguishable, older ones wait a little longer). */
+int b200nav_ctx_fence(b200nav_ctx* ctx, int* ticket);
+int b200nav_ctx_wait(b200nav_ctx* ctx, int ticket);
 void* b200nav_ctx_stream(b200nav_ctx* ctx);
 /* Last error text of this context (ctx == NULL: of the calling thread's last failed create call). */
 const char* b200nav_last_error(b200nav_ctx* ctx);
@@ -161,6 +166,14 @@ int b200nav_himm_update_batched_dev(b200nav_grid* grid, const char* layer, const
 int b200nav_himm_update_cloud_batched(b200nav_grid* grid, const char* layer, const double* host_origins,
                                       const float* host_xy, const uint8_t* host_clear_end,
                                       const int32_t* host_offsets, double* bbox);
+/* Same, but returns as soon as the copies and kernels are enqueued.  The host arrays must stay valid and unchanged
+ * until the work has completed (b200nav_ctx_wait on a later fence, b200nav_ctx_synchronize, or any synchronous call);
+ * use pinned memory, else the copies are staged synchronously.  Back-to-back asynchronous cycles overlap: the
+ * host->device copy of the next cloud runs while the tile kernel and the VFH+ kernel of the previous cycle execute
+ * (it only waits for the previous cycle's binning kernel, the last reader of the staged cloud). */
+int b200nav_himm_update_cloud_batched_async(b200nav_grid* grid, const char* layer, const double* host_origins,
+                                            const float* host_xy, const uint8_t* host_clear_end,
+                                            const int32_t* host_offsets);
 int b200nav_himm_update_cloud_batched_dev(b200nav_grid* grid, const char* layer, const double* dev_origins,
                                           const float* dev_xy, const uint8_t* dev_clear_end,
                                           const int32_t* dev_offsets, int total, int max_samples_per_robot);
@@ -248,6 +261,10 @@ int b200nav_vfh_update_grid(b200nav_vfh* vfh, b200nav_grid* grid, const char* la
 /* All robots; host arrays of n_robots entries. */
 int b200nav_vfh_update_batched(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
                                const b200nav_vfh_input* host_in, b200nav_command* host_out);
+/* Same, but returns once the input copy, the kernel and the copy of the commands into host_out are enqueued
+ * (host arrays: see b200nav_himm_update_cloud_batched_async). */
+int b200nav_vfh_update_batched_async(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
+                                     const b200nav_vfh_input* host_in, b200nav_command* host_out);
 /* Same with device arrays; asynchronous. */
 int b200nav_vfh_update_batched_dev(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
                                    const b200nav_vfh_input* dev_in, b200nav_command* dev_out);

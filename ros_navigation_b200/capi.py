@@ -68,6 +68,11 @@ _SIGNATURES = {
     "b200nav_grid_query_blocked": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "b200nav_grid_layer_written": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "b200nav_grid_layer_devptr": (C.c_void_p, [C.c_void_p, C.c_char_p]),
+    "b200nav_ctx_fence": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "b200nav_ctx_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200nav_himm_update_cloud_batched_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                          C.c_void_p]),
+    "b200nav_vfh_update_batched_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
     "b200nav_grid_has_layer": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_grid_layer_format": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_update": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -154,6 +159,16 @@ class Context:
 
     def synchronize(self):
         check(lib().b200nav_ctx_synchronize(self.h), self.h)
+
+    def fence(self):
+        """Mark the current end of the stream; returns a ticket for wait()."""
+        t = C.c_int()
+        check(lib().b200nav_ctx_fence(self.h, C.byref(t)), self.h)
+        return t.value
+
+    def wait(self, ticket):
+        """Block until everything enqueued before fence() -> ticket has completed."""
+        check(lib().b200nav_ctx_wait(self.h, int(ticket)), self.h)
 
     @property
     def stream(self):

@@ -50,6 +50,9 @@ struct b200nav_ctx {
   bool profiling = false;
   cudaStream_t copy_stream = nullptr;      /* host->device copies pipelined with the prep kernel */
   std::vector<cudaEvent_t> copy_events;
+  bool prep_done_valid = false;            /* copy_events[6] = "the last binning kernel has consumed the staged cloud" */
+  cudaEvent_t fences[8] = {nullptr};       /* b200nav_ctx_fence / b200nav_ctx_wait */
+  int fence_seq = 0;
   ProfSlot prof[PROF_KINDS];
   char err[512] = {0};
 };
@@ -123,6 +126,12 @@ struct b200nav_grid {
   RobotGeom* geom_dev = nullptr;
   std::map<std::string, std::shared_ptr<Layer>> layers;
   DevBuf samples, segs, offsets, occ, stats, beam_masks, errflag, origins, clearbuf, touched, worklist, counters;
+  /* cloud updates: offsets / origins double-buffered so that an asynchronous cycle can copy its own while the
+   * previous cycle's tile kernel still reads the other slot */
+  DevBuf offs2[2], orig2[2];
+  cudaEvent_t tile_done[2] = {nullptr, nullptr};
+  bool tile_done_set[2] = {false, false};
+  int cloud_slot = 0;
   DevBuf stage, convflag; /* float staging for upload / download of CODED layers; conversion "bad value" flag */
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
@@ -141,6 +150,11 @@ struct b200nav_vfh {
   uint32_t* d_masks = nullptr;
   int32_t* d_mtr = nullptr;
   DevBuf in_buf, out_buf, ranges_buf;
+  /* asynchronous batched updates: inputs double-buffered and copied on the context's copy stream */
+  DevBuf in2[2];
+  cudaEvent_t in_done[2] = {nullptr, nullptr}, in_ready = nullptr;
+  bool in_done_set[2] = {false, false};
+  int in_slot = 0;
   /* TMA descriptor cache: one per (layer pointer, geometry) */
   const float* tmap_layer = nullptr;
   int tmap_rows = 0, tmap_cols = 0, tmap_robots = 0, tmap_box_r = 0, tmap_box_c = 0;
@@ -621,7 +635,12 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
       cudaEventDestroy(p.second);
     }
   for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
-  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t e : ctx->fences)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200NAV_OK;
@@ -630,6 +649,23 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
 int b200nav_ctx_synchronize(b200nav_ctx* ctx) {
   if (!ctx) return B200NAV_EINVAL;
   return sync_stream(ctx);
+}
+
+int b200nav_ctx_fence(b200nav_ctx* ctx, int* ticket) {
+  if (!ctx || !ticket) return B200NAV_EINVAL;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaEvent_t& e = ctx->fences[ctx->fence_seq & 7];
+  if (!e) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventRecord(e, ctx->stream));
+  *ticket = ctx->fence_seq++;
+  return B200NAV_OK;
+}
+
+int b200nav_ctx_wait(b200nav_ctx* ctx, int ticket) {
+  if (!ctx || ticket < 0 || ticket >= ctx->fence_seq) return B200NAV_EINVAL;
+  /* a slot that was re-armed since marks a LATER point of the stream: waiting for it is still correct */
+  CUDA_TRY(ctx, cudaEventSynchronize(ctx->fences[ticket & 7]));
+  return B200NAV_OK;
 }
 
 void* b200nav_ctx_stream(b200nav_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -709,6 +745,11 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   g->layers.clear(); /* frees the device buffers */
   g->stage.release();
   g->convflag.release();
+  for (int i = 0; i < 2; i++) {
+    g->offs2[i].release();
+    g->orig2[i].release();
+    if (g->tile_done[i]) cudaEventDestroy(g->tile_done[i]);
+  }
   if (g->geom_dev) cudaFree(g->geom_dev);
   g->samples.release();
   g->segs.release();
@@ -1093,9 +1134,9 @@ int b200nav_himm_update_batched_dev(b200nav_grid* g, const char* layer, const b2
   return himm_launch(g, l, dev_samples, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot);
 }
 
-int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const double* host_origins,
-                                      const float* host_xy, const uint8_t* host_clear_end,
-                                      const int32_t* host_offsets, double* bbox) {
+static int himm_update_cloud_host(b200nav_grid* g, const char* layer, const double* host_origins,
+                                  const float* host_xy, const uint8_t* host_clear_end,
+                                  const int32_t* host_offsets, double* bbox, bool wait) {
   if (!g || !host_offsets || !host_origins) return B200NAV_EINVAL;
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
@@ -1112,33 +1153,46 @@ int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const 
   if (!host_xy) return B200NAV_EINVAL;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, g->samples.reserve(sizeof(float) * 2 * (size_t)total));
-  CUDA_TRY(ctx, g->offsets.reserve(sizeof(int32_t) * (size_t)(nr + 1)));
-  CUDA_TRY(ctx, g->origins.reserve(sizeof(double) * 2 * (size_t)nr));
-  CUDA_TRY(ctx, cudaMemcpyAsync(g->offsets.p, host_offsets, sizeof(int32_t) * (size_t)(nr + 1), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(g->origins.p, host_origins, sizeof(double) * 2 * (size_t)nr, cudaMemcpyHostToDevice, ctx->stream));
+  const int slot = g->cloud_slot;
+  g->cloud_slot ^= 1;
+  CUDA_TRY(ctx, g->offs2[slot].reserve(sizeof(int32_t) * (size_t)(nr + 1)));
+  CUDA_TRY(ctx, g->orig2[slot].reserve(sizeof(double) * 2 * (size_t)nr));
   CloudIn c;
-  c.origins = static_cast<const double*>(g->origins.p);
+  c.origins = static_cast<const double*>(g->orig2[slot].p);
   c.xy = static_cast<const float*>(g->samples.p);
   if (host_clear_end) {
     CUDA_TRY(ctx, g->clearbuf.reserve((size_t)total));
     c.clear_end = static_cast<const uint8_t*>(g->clearbuf.p);
   }
   HimmArgs a;
-  int rc = himm_setup(g, l, nullptr, static_cast<const int32_t*>(g->offsets.p), 0, nr, -1, total, max_per, c, a);
+  int rc = himm_setup(g, l, nullptr, static_cast<const int32_t*>(g->offs2[slot].p), 0, nr, -1, total, max_per, c, a);
   if (rc) return rc;
   /* Pipeline: the cloud is copied in groups of robots on a second stream while the prep kernel of the previous
    * group runs; the tile kernel starts when everything is binned. */
-  const int groups = (total >= (1 << 16) && nr >= 8) ? 4 : 1;
-  if (groups > 1 && !ctx->copy_stream) {
+  const bool piped = total >= (1 << 16) && nr >= 8;
+  /* synchronous call: 4 groups hide most of the copy behind the binning of the previous group; asynchronous call:
+   * the whole copy already overlaps the previous cycle's kernels, one group = one binning launch is cheaper */
+  const int groups = piped ? (wait ? 4 : 1) : 1;
+  if (piped && !ctx->copy_stream) {
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ctx->copy_events.resize(8);
     for (auto& e : ctx->copy_events) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  cudaStream_t cs = groups > 1 ? ctx->copy_stream : ctx->stream;
-  if (groups > 1) { /* the copy stream must not overwrite staging buffers still read by earlier work */
-    CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[7], ctx->stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->copy_events[7], 0));
+  cudaStream_t cs = piped ? ctx->copy_stream : ctx->stream;
+  /* offsets / origins go first and only wait for the tile kernel that last read this slot (two updates ago): they
+   * never queue behind the big cloud copy of a later cycle on the copy engine */
+  if (piped && g->tile_done_set[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, g->tile_done[slot], 0));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->offs2[slot].p, host_offsets, sizeof(int32_t) * (size_t)(nr + 1), cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->orig2[slot].p, host_origins, sizeof(double) * 2 * (size_t)nr, cudaMemcpyHostToDevice, cs));
+  if (piped) {
+    /* The copy stream must not overwrite staging buffers still read by earlier work.  After an asynchronous cloud
+     * update the only reader is that update's last binning kernel (event 6): this update's copies then overlap the
+     * previous update's tile kernel and whatever follows it on the main stream.  Otherwise: everything enqueued so
+     * far. */
+    if (!ctx->prep_done_valid) CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[6], ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->copy_events[6], 0));
   }
+  ctx->prep_done_valid = false;
   for (int gi = 0; gi < groups; gi++) {
     const int r_lo = (int)((long long)nr * gi / groups), r_hi = (int)((long long)nr * (gi + 1) / groups);
     const int b_lo = host_offsets[r_lo], b_hi = host_offsets[r_hi];
@@ -1149,15 +1203,24 @@ int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const 
         CUDA_TRY(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(g->clearbuf.p) + b_lo, host_clear_end + b_lo,
                                       (size_t)(b_hi - b_lo), cudaMemcpyHostToDevice, cs));
     }
-    if (groups > 1) {
+    if (piped) {
       CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[gi], cs));
       CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[gi], 0));
     }
     rc = himm_launch_prep(g, a, b_lo, b_hi, r_lo, r_hi);
     if (rc) return rc;
   }
+  if (piped && !wait) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[6], ctx->stream));
+    ctx->prep_done_valid = true;
+  }
   rc = himm_launch_tile(g, a);
   if (rc) return rc;
+  if (piped) {
+    if (!g->tile_done[slot]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&g->tile_done[slot], cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(g->tile_done[slot], ctx->stream));
+    g->tile_done_set[slot] = true;
+  }
   if (bbox)
     for (int r = 0; r < nr; r++) {
       double* bb = bbox + 4 * r;
@@ -1170,7 +1233,19 @@ int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const 
         bb[3] = std::max(std::max(bb[3], sy), ey);
       }
     }
-  return sync_stream(ctx);
+  return wait ? sync_stream(ctx) : B200NAV_OK;
+}
+
+int b200nav_himm_update_cloud_batched(b200nav_grid* g, const char* layer, const double* host_origins,
+                                      const float* host_xy, const uint8_t* host_clear_end,
+                                      const int32_t* host_offsets, double* bbox) {
+  return himm_update_cloud_host(g, layer, host_origins, host_xy, host_clear_end, host_offsets, bbox, true);
+}
+
+int b200nav_himm_update_cloud_batched_async(b200nav_grid* g, const char* layer, const double* host_origins,
+                                            const float* host_xy, const uint8_t* host_clear_end,
+                                            const int32_t* host_offsets) {
+  return himm_update_cloud_host(g, layer, host_origins, host_xy, host_clear_end, host_offsets, nullptr, false);
 }
 
 int b200nav_himm_update_cloud_batched_dev(b200nav_grid* g, const char* layer, const double* dev_origins,
@@ -1317,6 +1392,11 @@ int b200nav_vfh_destroy(b200nav_vfh* v) {
   cudaFree(v->dev.st);
   cudaFree(v->dev.ranges);
   v->in_buf.release();
+  for (int i = 0; i < 2; i++) {
+    v->in2[i].release();
+    if (v->in_done[i]) cudaEventDestroy(v->in_done[i]);
+  }
+  if (v->in_ready) cudaEventDestroy(v->in_ready);
   v->out_buf.release();
   v->ranges_buf.release();
   delete v;
@@ -1341,7 +1421,8 @@ int b200nav_vfh_get_max_turnrate(const b200nav_vfh* v, int speed) {
 }
 
 static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int robot0, int n,
-                        const b200nav_vfh_input* host_in, const double* host_ranges, b200nav_command* host_out) {
+                        const b200nav_vfh_input* host_in, const double* host_ranges, b200nav_command* host_out,
+                        bool wait = true) {
   b200nav_ctx* ctx = v->ctx;
   const Layer* lay = nullptr;
   if (g) {
@@ -1352,10 +1433,29 @@ static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int 
     lay = l;
   }
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  CUDA_TRY(ctx, v->in_buf.reserve(sizeof(b200nav_vfh_input) * (size_t)n));
   CUDA_TRY(ctx, v->out_buf.reserve(sizeof(b200nav_command) * (size_t)n));
-  CUDA_TRY(ctx, cudaMemcpyAsync(v->in_buf.p, host_in, sizeof(b200nav_vfh_input) * (size_t)n, cudaMemcpyHostToDevice,
-                                ctx->stream));
+  const b200nav_vfh_input* dev_in = nullptr;
+  int slot = -1;
+  if (!wait && ctx->copy_stream) {
+    /* pipelined cycles: the (small) input copy must not queue behind the next cycle's cloud on the copy engine, so
+     * it is issued on the copy stream as early as the slot's previous reader allows */
+    slot = v->in_slot;
+    v->in_slot ^= 1;
+    CUDA_TRY(ctx, v->in2[slot].reserve(sizeof(b200nav_vfh_input) * (size_t)n));
+    if (!v->in_ready) CUDA_TRY(ctx, cudaEventCreateWithFlags(&v->in_ready, cudaEventDisableTiming));
+    if (!v->in_done[slot]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&v->in_done[slot], cudaEventDisableTiming));
+    if (v->in_done_set[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, v->in_done[slot], 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(v->in2[slot].p, host_in, sizeof(b200nav_vfh_input) * (size_t)n,
+                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaEventRecord(v->in_ready, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, v->in_ready, 0));
+    dev_in = static_cast<const b200nav_vfh_input*>(v->in2[slot].p);
+  } else {
+    CUDA_TRY(ctx, v->in_buf.reserve(sizeof(b200nav_vfh_input) * (size_t)n));
+    CUDA_TRY(ctx, cudaMemcpyAsync(v->in_buf.p, host_in, sizeof(b200nav_vfh_input) * (size_t)n, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    dev_in = static_cast<const b200nav_vfh_input*>(v->in_buf.p);
+  }
   const double* dr = nullptr;
   if (host_ranges) {
     CUDA_TRY(ctx, v->ranges_buf.reserve(sizeof(double) * 2 * B200NAV_NRANGES * (size_t)n));
@@ -1363,12 +1463,15 @@ static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int 
                                   cudaMemcpyHostToDevice, ctx->stream));
     dr = static_cast<const double*>(v->ranges_buf.p);
   }
-  int rc = vfh_launch(v, g, lay, static_cast<const b200nav_vfh_input*>(v->in_buf.p), dr,
-                      static_cast<b200nav_command*>(v->out_buf.p), robot0, n);
+  int rc = vfh_launch(v, g, lay, dev_in, dr, static_cast<b200nav_command*>(v->out_buf.p), robot0, n);
   if (rc) return rc;
+  if (slot >= 0) {
+    CUDA_TRY(ctx, cudaEventRecord(v->in_done[slot], ctx->stream));
+    v->in_done_set[slot] = true;
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(host_out, v->out_buf.p, sizeof(b200nav_command) * (size_t)n, cudaMemcpyDeviceToHost,
                                 ctx->stream));
-  return sync_stream(ctx);
+  return wait ? sync_stream(ctx) : B200NAV_OK;
 }
 
 int b200nav_vfh_update_ranges(b200nav_vfh* v, int robot, const double* ranges361x2, const b200nav_vfh_input* in,
@@ -1388,6 +1491,13 @@ int b200nav_vfh_update_batched(b200nav_vfh* v, b200nav_grid* g, const char* laye
   if (!v || !g || !host_in || !host_out) return B200NAV_EINVAL;
   if (g->n_robots != v->n_robots) return set_err(v->ctx, B200NAV_EINVAL, "grid and vfh robot counts differ");
   return vfh_run_host(v, g, layer, 0, v->n_robots, host_in, nullptr, host_out);
+}
+
+int b200nav_vfh_update_batched_async(b200nav_vfh* v, b200nav_grid* g, const char* layer,
+                                     const b200nav_vfh_input* host_in, b200nav_command* host_out) {
+  if (!v || !g || !host_in || !host_out) return B200NAV_EINVAL;
+  if (g->n_robots != v->n_robots) return set_err(v->ctx, B200NAV_EINVAL, "grid and vfh robot counts differ");
+  return vfh_run_host(v, g, layer, 0, v->n_robots, host_in, nullptr, host_out, false);
 }
 
 int b200nav_vfh_update_batched_dev(b200nav_vfh* v, b200nav_grid* g, const char* layer,

@@ -303,33 +303,35 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, int v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-struct CodeView { /* shared memory, one byte per cell */
+struct CodeView { /* shared memory, one byte per cell; offsets are shared-space byte addresses (bias()) */
   uint32_t base; /* shared-space address of the tile */
-  __device__ __forceinline__ bool sensitive(int off) const { return lds_u8(base + off) >= 2; }
-  __device__ __forceinline__ void set_free(int off) const { sts_u8(base + off, 1); }
+  __device__ __forceinline__ int bias() const { return (int)base; }
+  __device__ __forceinline__ bool sensitive(int off) const { return lds_u8(off) >= 2; }
+  __device__ __forceinline__ void set_free(int off) const { sts_u8(off, 1); }
   __device__ __forceinline__ void clear_n(int off, int n, bool mark) const {
-    int c = max(lds_u8(base + off) - n, 1);
+    int c = max(lds_u8(off) - n, 1);
     if (mark) c = (c <= 16) ? c + 3 : c;
-    sts_u8(base + off, c);
+    sts_u8(off, c);
   }
   /* clears and marks of several beams on one cell, in lane order: lanes in `group`, those in `marks` also mark */
   __device__ __forceinline__ void clear_seq(int off, unsigned group, unsigned marks) const {
-    int c = lds_u8(base + off);
+    int c = lds_u8(off);
     while (group) {
       const unsigned bit = group & (0u - group);
       group ^= bit;
       c = max(c - 1, 1);
       if (marks & bit) c = (c <= 16) ? c + 3 : c;
     }
-    sts_u8(base + off, c);
+    sts_u8(off, c);
   }
   __device__ __forceinline__ void mark(int off) const {
-    const int c = lds_u8(base + off);
-    sts_u8(base + off, (c <= 1) ? 4 : ((c <= 16) ? c + 3 : c));
+    const int c = lds_u8(off);
+    sts_u8(off, (c <= 1) ? 4 : ((c <= 16) ? c + 3 : c));
   }
 };
 struct FloatView { /* global memory, in place (tiles with values outside the HIMM set) */
   volatile float* p;
+  __device__ __forceinline__ int bias() const { return 0; }
   __device__ __forceinline__ bool sensitive(int) const { return true; }
   __device__ __forceinline__ void set_free(int off) const { p[off] = 0.0f; }
   __device__ __forceinline__ void clear_n(int off, int n, bool mark) const {
@@ -377,12 +379,12 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
     nb.r0 = -1;
     nb.mr = -1;
     if (j + 32 < n_list) nb = segs[list[j + 32]];
-    int my_len = 0, my_t0 = 0, my_off0 = 0, my_rem0 = 0, my_dm = 0, my_dn = 0, my_add = 0, my_den = 1, my_moff = -1;
+    int my_len = 0, my_t0 = 0, my_off0 = view.bias(), my_rem0 = 0, my_dm = 0, my_dn = 0, my_add = 0, my_den = 1, my_moff = -1;
     int my_r0 = -1, my_c0 = -1;
     bool mark_at_end = false; /* the mark cell is the last cell of my segment */
     if (have) {
       const bool has_mark = b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1;
-      if (has_mark) my_moff = (b.mc - C0) * pitch + (b.mr - R0);
+      if (has_mark) my_moff = view.bias() + (b.mc - C0) * pitch + (b.mr - R0);
       if (b.r0 >= 0) {
         const LineForm f = line_form(b);
         int t0, t1;
@@ -393,7 +395,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           my_rem0 = (int)(x0 - q0 * den);
           const int mj = f.m0 + f.sm * t0, mn = f.n0 + f.sn * (int)q0;
           const int r = f.row_major ? mj : mn, c = f.row_major ? mn : mj;
-          my_off0 = (c - C0) * pitch + (r - R0);
+          my_off0 = view.bias() + (c - C0) * pitch + (r - R0);
           my_dm = f.row_major ? f.sm : f.sm * pitch;
           my_dn = f.row_major ? f.sn * pitch : f.sn;
           my_add = f.add;
@@ -435,16 +437,22 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           else view.clear_seq(o, group, marks);
         }
       };
-      /* RINGS steps (disjoint rings of cells) per iteration */
+      /* RINGS steps (disjoint rings of cells) per iteration.  Cells of different steps are different cells, so
+       * only the reads and writes of ONE iteration can meet: a single warp barrier between its read half and its
+       * write half orders them. */
       constexpr int RINGS = 4;
-      for (int it = tmax - tmin; it >= 0; it -= RINGS, k += RINGS) {
+      const int n_iter = (tmax - tmin) / RINGS;
+      const int mark_iter = (my_moff >= 0) ? (mark_k - k) / RINGS : -1; /* iteration in which this lane marks */
+      for (int i = 0; i <= n_iter; i++, k += RINGS) {
         int offs[RINGS];
-        bool sens = false;
+        bool hot[RINGS]; /* my cell of ring r holds a value that counts visits (code >= 2) */
+        bool sens = (i == mark_iter);
 #pragma unroll
         for (int r = 0; r < RINGS; r++) {
           offs[r] = off;
           const bool on = (unsigned)(k + r) <= span;
-          sens = sens || (on && (view.sensitive(off) || k + r == mark_k));
+          hot[r] = on && view.sensitive(off);
+          sens = sens || hot[r];
           if ((unsigned)(k + r) < span) { /* my next cell (stay on the last one) */
             rem += my_add;
             off += my_dm;
@@ -462,12 +470,13 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
         } else {
 #pragma unroll
           for (int r = 0; r < RINGS; r++) {
-            ring_exact((unsigned)(k + r) <= span, offs[r], k + r == mark_k);
-            __syncwarp();
+            const bool on = (unsigned)(k + r) <= span, marking = k + r == mark_k;
+            if (__any_sync(0xffffffffu, hot[r] || (on && marking))) ring_exact(on, offs[r], marking);
+            else if (on) view.set_free(offs[r]);
           }
         }
-        __syncwarp();
       }
+      __syncwarp(); /* the next batch may read any cell this one wrote */
     } else {
       /* ---- general schedule ---- */
       while (active) {

@@ -123,6 +123,12 @@ class DeviceGridMap:
                                                       None if ce is None else ce.ctypes.data, offsets.ctypes.data,
                                                       ptr(bbox)), self.ctx.h)
 
+    def himm_update_cloud_batched_async(self, layer, origins, xy, clear_end, offsets):
+        """Enqueue-only form: the arguments must be host buffers (pinned torch tensors / numpy arrays) that stay valid
+        and unchanged until the context has caught up (Context.wait / synchronize)."""
+        check(lib().b200nav_himm_update_cloud_batched_async(self.h, layer.encode(), ptr(origins), ptr(xy),
+                                                            ptr(clear_end), ptr(offsets)), self.ctx.h)
+
     def himm_update_cloud_batched_dev(self, layer, dev_origins, dev_xy, dev_clear_end, dev_offsets, total,
                                       max_per_robot):
         check(lib().b200nav_himm_update_cloud_batched_dev(self.h, layer.encode(), ptr(dev_origins), ptr(dev_xy),

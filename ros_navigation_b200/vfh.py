@@ -101,6 +101,11 @@ class VFH:
               self.ctx.h)
         return out
 
+    def update_batched_async(self, grid, layer, host_inputs, host_out):
+        """Enqueue-only form of update_batched: host buffers (pinned) in and out, valid until the context caught up."""
+        check(lib().b200nav_vfh_update_batched_async(self.h, grid.h, layer.encode(), ptr(host_inputs), ptr(host_out)),
+              self.ctx.h)
+
     def update_batched_dev(self, grid, layer, dev_inputs, dev_out):
         check(lib().b200nav_vfh_update_batched_dev(self.h, grid.h, layer.encode(), ptr(dev_inputs), ptr(dev_out)),
               self.ctx.h)

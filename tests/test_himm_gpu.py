@@ -300,6 +300,57 @@ def test_cloud_form_pipelined_copy_groups(ctx):
     dg.close()
 
 
+def test_async_cycles_overlap_and_match_synchronous_calls(ctx):
+    """b200nav_himm_update_cloud_batched_async + b200nav_vfh_update_batched_async from pinned host buffers, several
+    cycles in flight (the cloud copy of cycle i+1 overlaps the kernels of cycle i): grids and commands equal those of
+    the synchronous calls on a second grid."""
+    import torch
+    from ros_navigation_b200 import VFH, DeviceGridMap, capi
+    rng = np.random.default_rng(17)
+    n_robots, beams, cycles = 96, 720, 6
+    grids = [DeviceGridMap(ctx, (12.8, 12.8), 0.05, n_robots=n_robots, layers=("laser",)) for _ in range(2)]
+    vfhs = [VFH(ctx, n_robots=n_robots) for _ in range(2)]
+    data, tickets = [], []
+    for c in range(cycles):
+        origins = rng.uniform(-3, 3, (n_robots, 2))
+        offsets = np.arange(n_robots + 1, dtype=np.int32) * beams
+        assert offsets[-1] >= 65536
+        ang = np.tile(np.linspace(-np.pi, np.pi, beams, endpoint=False), n_robots)
+        rad = rng.uniform(0.3, 5.0, offsets[-1])
+        own = np.repeat(np.arange(n_robots), beams)
+        xy = np.stack([origins[own, 0] + rad * np.cos(ang), origins[own, 1] + rad * np.sin(ang)], 1).astype(np.float32)
+        clear = (rng.random(offsets[-1]) < 0.05).astype(np.uint8)
+        inp = np.zeros(n_robots, capi.VFH_INPUT_DTYPE)
+        inp["x"], inp["y"], inp["yaw"], inp["dt"] = origins[:, 0], origins[:, 1], rng.uniform(-3, 3, n_robots), 0.2
+        inp["current_speed"], inp["goal_direction"], inp["goal_distance"], inp["goal_tolerance"] = 100, 90.0, 3000.0, 250.0
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        data.append(dict(origins=pin(origins), xy=pin(xy), clear=pin(clear), offsets=pin(offsets),
+                         inp=pin(inp.view(np.uint8).reshape(n_robots, -1)), inp_np=inp,
+                         out=torch.zeros(n_robots, 16, dtype=torch.uint8).pin_memory()))
+    for c, d in enumerate(data):  # enqueue everything without waiting
+        grids[0].himm_update_cloud_batched_async("laser", d["origins"], d["xy"], d["clear"], d["offsets"])
+        vfhs[0].update_batched_async(grids[0], "laser", d["inp"], d["out"])
+        tickets.append(ctx.fence())
+    want = []
+    for d in data:
+        grids[1].himm_update_cloud_batched("laser", d["origins"].numpy(), d["xy"].numpy(), d["clear"].numpy(),
+                                           d["offsets"].numpy())
+        want.append(vfhs[1].update_batched(grids[1], "laser", d["inp_np"]))
+    for c in (3, 0, 5):
+        ctx.wait(tickets[c])
+        got = data[c]["out"].numpy().view(capi.COMMAND_DTYPE).reshape(-1)
+        assert np.array_equal(got, want[c]), "commands of cycle %d" % c
+    ctx.synchronize()
+    for c in range(cycles):
+        assert np.array_equal(data[c]["out"].numpy().view(capi.COMMAND_DTYPE).reshape(-1), want[c])
+    for r in range(0, n_robots, 7):
+        assert_layers_equal(grids[0].download("laser", robot=r), grids[1].download("laser", robot=r), "robot %d" % r)
+    with pytest.raises(capi.B200NavError):
+        ctx.wait(10 ** 6)
+    for x in vfhs + grids:
+        x.close()
+
+
 def test_c2_sized_grid_scan_sequence(ctx):
     """BASELINE config 2 geometry: 2048 x 2048 @ 5 cm, 1080-beam / 270 deg scans up to 30 m."""
     import torch
