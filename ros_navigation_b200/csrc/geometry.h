@@ -375,5 +375,26 @@ B200_HD bool clip_line_to_rect(const LineForm& f, int rlo, int rhi, int clo, int
  * true quotient at least 0.5/den (>= 1.5e-5) away from an integer while the float error stays below 5e-6. */
 B200_HD int small_quotient(int x, float rcp_den) { return (int)(((float)x + 0.5f) * rcp_den); }
 
+/* Exact fixed-point form of the Bresenham recurrence of LineForm (geometry.h): step t of a line visits minor index
+ *   q(t) = floor(((den >> 1) + t * add) / den),   0 <= t <= den,  add <= den.
+ * With S = ceil(add * 2^32 / den) and B = ceil((den >> 1) * 2^32 / den), X(t) = B + t * S (64 bit) satisfies
+ *   X(t) / 2^32 = exact + e,  0 <= e < (t + 1) / 2^32 <= (den + 1) / 2^32,
+ * and the exact value's fractional part is a multiple of 1/den, at most 1 - 1/den.  So floor(X(t) / 2^32) = q(t)
+ * whenever (den + 1) / 2^32 < 1 / den, i.e. for every den <= 65535 (grids have at most 32767 cells per side).
+ * The walk then is: frac += S; carry -> one minor step.  add == den (45 degrees) would need S = 2^32: `diag` folds
+ * the minor step into the major one instead.  Verified exhaustively against the integer recurrence in
+ * tests/cpp/host_checks.cpp. */
+B200_HD void dda_init(unsigned add, unsigned den, unsigned& S, unsigned& B, bool& diag) {
+  diag = add >= den;
+  /* two 16-bit long-division steps: add, den < 2^16 */
+  const unsigned n1 = add << 16, hi = n1 / den, r1 = n1 - hi * den;
+  const unsigned n2 = r1 << 16, lo = n2 / den, r2 = n2 - lo * den;
+  S = diag ? 0u : ((hi << 16) + lo + (r2 != 0u ? 1u : 0u));
+  B = diag ? 0u : 0x80000000u - ((den & 1u) ? 0x80000000u / den : 0u);
+}
+B200_HD unsigned long long dda_at(unsigned S, unsigned B, unsigned t) {
+  return (unsigned long long)B + (unsigned long long)t * (unsigned long long)S;
+}
+
 }  // namespace b200nav
 #endif

@@ -380,7 +380,9 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
     nb.mr = -1;
     if (j + 32 < n_list) nb = segs[list[j + 32]];
     int my_len = 0, my_t0 = 0, my_off0 = view.bias(), my_rem0 = 0, my_dm = 0, my_dn = 0, my_add = 0, my_den = 1, my_moff = -1;
-    int my_r0 = -1, my_c0 = -1;
+    int my_r0 = -1, my_c0 = -1, my_q0 = 0;
+    unsigned my_S = 0u, my_B = 0u; /* fixed-point slope / half offset (dda_init) */
+    bool my_diag = false;
     bool mark_at_end = false; /* the mark cell is the last cell of my segment */
     if (have) {
       const bool has_mark = b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1;
@@ -390,8 +392,10 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
         int t0, t1;
         if (clip_line_to_rect(f, R0, R1, C0, C1, t0, t1)) {
           const unsigned den = (unsigned)max(f.den, 1);
+          dda_init((unsigned)f.add, den, my_S, my_B, my_diag);
           const unsigned x0 = (unsigned)(f.den >> 1) + (unsigned)t0 * (unsigned)f.add;
-          const unsigned q0 = x0 / den;
+          const unsigned q0 = my_diag ? (unsigned)t0 : (unsigned)(dda_at(my_S, my_B, (unsigned)t0) >> 32); /* == x0 / den */
+          my_q0 = my_diag ? 0 : (int)q0;
           my_rem0 = (int)(x0 - q0 * den);
           const int mj = f.m0 + f.sm * t0, mn = f.n0 + f.sn * (int)q0;
           const int r = f.row_major ? mj : mn, c = f.row_major ? mn : mj;
@@ -425,7 +429,14 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
       const unsigned span = (my_len > 0) ? (unsigned)(my_len - 1) : 0u;
       const int last = (my_len > 0) ? my_t0 + my_len - 1 : -0x7fffffff;
       const int tmin = __reduce_min_sync(0xffffffffu, first), tmax = __reduce_max_sync(0xffffffffu, last);
-      int off = my_off0, rem = my_rem0; /* `off` always addresses a cell of this tile, also while the lane idles */
+      /* every lane starts at step tmin of ITS line (possibly before it enters the tile: such cells are never
+       * dereferenced) and then steps unconditionally: frac += S, the carry is the minor step */
+      const int back = (my_len > 0) ? my_t0 - tmin : 0;
+      const unsigned long long xs = dda_at(my_S, my_B, (unsigned)((my_len > 0) ? tmin : 0));
+      unsigned frac = (unsigned)xs;
+      const int qs = my_diag ? 0 : (int)(xs >> 32);
+      const int step_plain = my_diag ? my_dm + my_dn : my_dm, step_carry = step_plain + my_dn;
+      int off = my_off0 - back * step_plain - (my_q0 - qs) * my_dn;
       const int mark_k = (my_moff >= 0) ? (int)span : -1; /* step (relative to `first`) that also marks */
       int k = (my_len > 0) ? tmin - first : -0x40000000;
       /* exact application of one ring (all lanes at the same step): group lanes by cell, lowest lane applies */
@@ -453,14 +464,9 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           const bool on = (unsigned)(k + r) <= span;
           hot[r] = on && view.sensitive(off);
           sens = sens || hot[r];
-          if ((unsigned)(k + r) < span) { /* my next cell (stay on the last one) */
-            rem += my_add;
-            off += my_dm;
-            if (rem >= my_den) {
-              rem -= my_den;
-              off += my_dn;
-            }
-          }
+          const unsigned nf = frac + my_S;
+          off += (nf < frac) ? step_carry : step_plain;
+          frac = nf;
         }
         __syncwarp(); /* all reads of this iteration are done before any lane writes (memory-model order) */
         if (!__any_sync(0xffffffffu, sens)) {

@@ -253,8 +253,68 @@ static int check_vfh_tables(const b200nav_vfh_params& p) {
   return 0;
 }
 
+/* (4) dda_init / dda_at (the fan walk's fixed-point stepping) against the integer Bresenham recurrence:
+ *     q(t) = floor(((den >> 1) + t * add) / den) for every step of every (den, add) tested; also started mid-line
+ *     the way the tile kernel does (state taken at t0, then frac += S with carry). */
+static int check_dda_pair(unsigned den, unsigned add) {
+  unsigned S, B;
+  bool diag;
+  b200nav::dda_init(add, den, S, B, diag);
+  const unsigned h = den >> 1;
+  /* closed form at every t */
+  for (unsigned t = 0; t <= den; t++) {
+    const unsigned want = (unsigned)(((unsigned long long)h + (unsigned long long)t * add) / den);
+    const unsigned got = diag ? t : (unsigned)(b200nav::dda_at(S, B, t) >> 32);
+    g_checks++;
+    if (want != got) {
+      printf("dda closed form den=%u add=%u t=%u: want %u got %u\n", den, add, t, want, got);
+      return 1;
+    }
+  }
+  /* incremental from a start in the middle */
+  const unsigned t0 = den / 3;
+  unsigned frac = (unsigned)b200nav::dda_at(S, B, t0);
+  unsigned q = diag ? t0 : (unsigned)(b200nav::dda_at(S, B, t0) >> 32);
+  for (unsigned t = t0; t < den; t++) {
+    const unsigned nf = frac + S;
+    q += diag ? 1u : (nf < frac ? 1u : 0u);
+    frac = nf;
+    const unsigned want = (unsigned)(((unsigned long long)h + (unsigned long long)(t + 1) * add) / den);
+    g_checks++;
+    if (want != q) {
+      printf("dda walk den=%u add=%u t=%u: want %u got %u\n", den, add, t + 1, want, q);
+      return 1;
+    }
+  }
+  return 0;
+}
+
+static int check_dda(unsigned seed, int iters) {
+  const unsigned full = iters > 100 ? 900u : 400u; /* every add for every den up to here */
+  for (unsigned den = 1; den <= full; den++)
+    for (unsigned add = 0; add <= den; add++)
+      if (check_dda_pair(den, add)) return 1;
+  /* extremes of every 5th longer line, and random slopes up to the largest grid (32767 cells) */
+  for (unsigned den = full + 1; den <= 32767u; den += 5) {
+    const unsigned adds[] = {0u, 1u, 2u, den / 2 - 1, den / 2, den / 2 + 1, den - 2, den - 1, den};
+    if (den % 97 == 0)
+      for (unsigned a : adds)
+        if (check_dda_pair(den, a)) return 1;
+  }
+  std::mt19937 rng(seed);
+  for (int i = 0; i < 300 * (iters > 100 ? 5 : 1); i++) {
+    const unsigned den = 1u + rng() % 32767u, add = rng() % (den + 1u);
+    if (check_dda_pair(den, add)) return 1;
+  }
+  for (unsigned den : {32767u, 32766u, 65535u, 65534u, 40001u})
+    for (unsigned add : {1u, den / 3, den - 1, den})
+      if (check_dda_pair(den, add)) return 1;
+  return 0;
+}
+
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 40;
+  if (check_dda(4242u, iters)) return 1;
   if (check_f64_helpers(777u, 200000LL * (iters > 100 ? 10 : 1))) return 1;
   if (check_geometry(12345u, iters)) return 1;
   b200nav_vfh_params p;
