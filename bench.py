@@ -31,6 +31,7 @@ METRIC = "laser scans/sec fused into HIMM grid + VFH+ steering decisions/sec"
 UNIT = "scans/s (each scan = 1 HIMM grid update + 1 VFH+ decision)"
 N_CYCLES = 8          # distinct pre-generated cycles replayed round-robin (inputs > L2 at N=1)
 L2_FLUSH_BYTES = 256 << 20
+L2_FLUSH_LIGHT_BYTES = 160 << 20   # > 126 MB of L2
 
 
 def log(*a):
@@ -325,7 +326,7 @@ class GpuArm:
             i = first + k
             c, slot = i % N_CYCLES, k & 1
             if flush:
-                flush_l2(self)
+                flush_l2_light(self)
             self.grid.himm_update_cloud_batched_async("laser", self.h_origins[c], self.h_xy[c], self.h_clear[c],
                                                       self.h_offsets[c])
             if self.exchange is None:
@@ -352,6 +353,12 @@ class GpuArm:
         self.step_himm_only(c)
         visits, marks, beams = self.grid.himm_last_stats()
         return 8 * visits + 8 * marks + 36 * beams, visits, marks, beams
+
+
+def flush_l2_light(arm):
+    """In-stream flush for the pipelined end-to-end loop: write a buffer larger than L2 (160 MiB > 126 MB).  The
+    write-back of these lines happens inside the timed region like everything else there."""
+    arm.flush[:L2_FLUSH_LIGHT_BYTES].zero_()
 
 
 def flush_l2(arm):
@@ -430,7 +437,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         stream.synchronize()
         t0 = time.perf_counter()
         for k in range(args.steps):
-            flush_l2(arm)
+            flush_l2_light(arm)
         stream.synchronize()
         flush_s = time.perf_counter() - t0
         if world > 1:
@@ -470,8 +477,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / args.steps,
                 "how": "wall clock over all timed cycles through the asynchronous C-ABI calls, 2 cycles in flight: pinned "
-                       "host buffers in, commands back to pinned host memory; the in-stream L2 flushes are INSIDE "
-                       "this time",
+                       "host buffers in, commands back to pinned host memory; L2 is flushed in-stream before every "
+                       "cycle (160 MiB write) and that flush is INSIDE this time",
                 "l2_flush_ms_per_step": flush_s * 1000.0 / args.steps},
         "gpu_launches": int(launches),
         "clocks": clk,

@@ -386,10 +386,11 @@ B200_HD int small_quotient(int x, float rcp_den) { return (int)(((float)x + 0.5f
  * tests/cpp/host_checks.cpp. */
 B200_HD void dda_init(unsigned add, unsigned den, unsigned& S, unsigned& B, bool& diag) {
   diag = add >= den;
-  /* two 16-bit long-division steps: add, den < 2^16 */
+  /* S = ceil(add * 2^32 / den) by two 16-bit long-division steps (add, den < 2^16) */
   const unsigned n1 = add << 16, hi = n1 / den, r1 = n1 - hi * den;
   const unsigned n2 = r1 << 16, lo = n2 / den, r2 = n2 - lo * den;
   S = diag ? 0u : ((hi << 16) + lo + (r2 != 0u ? 1u : 0u));
+  /* B = ceil((den >> 1) * 2^32 / den): 2^31 for even den, 2^31 - floor(2^31 / den) for odd den */
   B = diag ? 0u : 0x80000000u - ((den & 1u) ? 0x80000000u / den : 0u);
 }
 B200_HD unsigned long long dda_at(unsigned S, unsigned B, unsigned t) {

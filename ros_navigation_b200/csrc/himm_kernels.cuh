@@ -439,15 +439,6 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
       int off = my_off0 - back * step_plain - (my_q0 - qs) * my_dn;
       const int mark_k = (my_moff >= 0) ? (int)span : -1; /* step (relative to `first`) that also marks */
       int k = (my_len > 0) ? tmin - first : -0x40000000;
-      /* exact application of one ring (all lanes at the same step): group lanes by cell, lowest lane applies */
-      auto ring_exact = [&](bool on, int o, bool marking) {
-        const unsigned group = __match_any_sync(0xffffffffu, on ? o : -1 - lane);
-        const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
-        if (on && (group & ((1u << lane) - 1u)) == 0u) {
-          if (marks == 0u) view.clear_n(o, __popc(group), false);
-          else view.clear_seq(o, group, marks);
-        }
-      };
       /* RINGS steps (disjoint rings of cells) per iteration.  Cells of different steps are different cells, so
        * only the reads and writes of ONE iteration can meet: a single warp barrier between its read half and its
        * write half orders them. */
@@ -477,8 +468,16 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
 #pragma unroll
           for (int r = 0; r < RINGS; r++) {
             const bool on = (unsigned)(k + r) <= span, marking = k + r == mark_k;
-            if (__any_sync(0xffffffffu, hot[r] || (on && marking))) ring_exact(on, offs[r], marking);
-            else if (on) view.set_free(offs[r]);
+            if (__any_sync(0xffffffffu, hot[r] || (on && marking))) {
+              const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1 - lane);
+              const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
+              if (on && (group & ((1u << lane) - 1u)) == 0u) {
+                if (marks == 0u) view.clear_n(offs[r], __popc(group), false);
+                else view.clear_seq(offs[r], group, marks);
+              }
+            } else if (on) {
+              view.set_free(offs[r]);
+            }
           }
         }
       }
@@ -853,7 +852,7 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
   }
   __syncwarp();
   uint32_t phase = 0; /* mbarrier phase parity of the next copy-in */
-
+  /* work items are claimed one ahead: the atomic's round trip hides behind the current item */
   for (;;) {
     int w = 0;
     if (lane == 0) w = atomicAdd(&a.counters[1], 1);
