@@ -67,6 +67,29 @@ for kern in ("tile", "prep", "vfh"):
     agg = sorted(((sum(fl(r[hdr.index(h)]) for r in data), h) for h in stalls), reverse=True)[:6]
     lines.append("warp-state samples: " + ", ".join("%s %.1f%%" % (h, 100 * v / tot) for v, h in agg))
     lines.append("")
+    # hottest CUDA source lines (ncu --page source --print-source sass,cuda)
+    src2 = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"],
+                          capture_output=True, text=True).stdout
+    cur_file, hdr2, per_line = None, None, []
+    for r in csv.reader(src2.splitlines()):
+        if len(r) == 2 and r[0] == "File Path":
+            cur_file = r[1].split("/")[-1]
+        elif r and r[0] == "Line No":
+            hdr2 = r
+        elif hdr2 and len(r) == len(hdr2) and r[0] not in ("", "Line No"):
+            per_line.append((cur_file, r))
+    if per_line:
+        s2, i2 = hdr2.index("# Samples"), hdr2.index("Instructions Executed")
+        ts = sum(fl(r[s2]) for _, r in per_line) or 1.0
+        ti = sum(fl(r[i2]) for _, r in per_line) or 1.0
+        lines.append("hottest source lines (share of samples / of executed warp instructions):")
+        lines.append("")
+        lines.append("| file:line | samples | instr | source |")
+        lines.append("|---|---|---|---|")
+        for f, r in sorted(per_line, key=lambda fr: -fl(fr[1][s2]))[:12]:
+            lines.append("| %s:%s | %.1f%% | %.1f%% | `%s` |" % (f, r[0], 100 * fl(r[s2]) / ts, 100 * fl(r[i2]) / ti,
+                                                             r[1].strip()[:90].replace("|", "\\|")))
+        lines.append("")
 open(os.path.join(P, "ncu_summary_%s.md" % tag), "w").write("\n".join(lines))
 if traffic:
     tj = os.path.join(P, "traffic.json")
