@@ -374,6 +374,7 @@ int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, c
   a.beam_hi = total;
   a.rel_lo = 0;
   a.rel_hi = n_active;
+  a.max_per_robot = max_per_robot;
   a.tiles_r = (g->dims.rows + TileCfg::kTileR - 1) / TileCfg::kTileR;
   a.tiles_c = (g->dims.cols + TileCfg::kTileC - 1) / TileCfg::kTileC;
   a.chunk_beams = std::min(HIMM_CHUNK, std::max(32, (max_per_robot + 31) & ~31));
@@ -407,7 +408,10 @@ int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int 
   a.rel_hi = rel_hi;
   {
     ProfScope ps(ctx, PROF_HIMM_PREP);
-    himm_prep_kernel<<<(beam_hi - beam_lo + 127) / 128, 128, 0, ctx->stream>>>(a);
+    const int n_rel = rel_hi - rel_lo;
+    const unsigned gy = (unsigned)std::min(n_rel, 32768), gz = (unsigned)((n_rel + 32767) / 32768);
+    dim3 grid((unsigned)std::max(1, (a.max_per_robot + 127) / 128), gy, gz);
+    himm_prep_kernel<<<grid, 128, 0, ctx->stream>>>(a);
   }
   return check_launch(ctx, "himm_prep_kernel");
 }

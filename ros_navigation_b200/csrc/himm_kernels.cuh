@@ -67,8 +67,9 @@ struct HimmArgs {
   int single_n;                   /* >= 0: single-robot mode, samples [0, n)      */
   int total;                      /* total samples                                */
   /* the prep kernel may be launched per group of robots (pipelined with the host->device copies):
-   * it then handles beams [beam_lo, beam_hi) which belong to robots [rel_lo, rel_hi) of this update */
+   * it then handles robots [rel_lo, rel_hi) of this update (their beams are [beam_lo, beam_hi)) */
   int beam_lo, beam_hi, rel_lo, rel_hi;
+  int max_per_robot;              /* upper bound of the beams of one robot (sizes the prep grid) */
   int tiles_r, tiles_c;           /* tiles per grid                               */
   int n_chunks;                   /* chunks per robot                             */
   int chunk_beams;                /* beams per chunk: multiple of 32, <= HIMM_CHUNK */
@@ -84,47 +85,24 @@ struct HimmArgs {
  * word equals its left neighbour's joins that neighbour's run, and the head of each run issues one RED.OR with the
  * run's (contiguous) bits.  ~10x fewer L2 reductions than one per (beam, tile).
  * ------------------------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(128, 12) himm_prep_kernel(HimmArgs a) {
-  const int i = a.beam_lo + blockIdx.x * blockDim.x + threadIdx.x;
+#ifndef HIMM_PREP_BLOCKS
+#define HIMM_PREP_BLOCKS 12
+#endif
+__global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmArgs a) {
+  /* grid = (blocks per robot, robots of this launch): the robot is the block's y index - no search through the
+   * offsets - and a warp never straddles two robots */
   const int lane = threadIdx.x & 31;
-  const bool valid = i < a.beam_hi;
-  int rel = 0, beg = 0;
+  const int rel = a.rel_lo + (int)blockIdx.y + (int)gridDim.y * (int)blockIdx.z;
+  if (rel >= a.rel_hi) return;
+  int beg = 0, end = a.single_n;
   if (a.single_n < 0) {
-    /* robot of beam i = last r with offsets[r] <= i.  Lane 0 of the warp resolves the warp's first beam
-     * (proportional first guess - robots usually carry similar beam counts -, a short linear walk, a binary search
-     * only if the walk does not settle), then every lane walks forward from there. */
-    const int i0 = min(i, a.beam_hi - 1);
-    int lo = a.rel_lo;
-    if (lane == 0) {
-      lo = a.rel_lo + (int)(((long long)(i0 - a.beam_lo) * (a.rel_hi - a.rel_lo)) / (a.beam_hi - a.beam_lo));
-      int steps = 0;
-      while (lo > a.rel_lo && __ldg(&a.offsets[lo]) > i0 && steps < 6) {
-        lo--;
-        steps++;
-      }
-      while (lo + 1 < a.rel_hi && __ldg(&a.offsets[lo + 1]) <= i0 && steps < 6) {
-        lo++;
-        steps++;
-      }
-      if (__ldg(&a.offsets[lo]) > i0 || (lo + 1 < a.rel_hi && __ldg(&a.offsets[lo + 1]) <= i0)) {
-        int l2 = a.rel_lo, hi = a.rel_hi;
-        while (hi - l2 > 1) {
-          const int mid = (l2 + hi) >> 1;
-          if (__ldg(&a.offsets[mid]) <= i0) l2 = mid;
-          else hi = mid;
-        }
-        lo = l2;
-      }
-    }
-    lo = __shfl_sync(0xffffffffu, lo, 0);
-    int nxt = __ldg(&a.offsets[lo + 1]);
-    while (nxt <= i0 && lo + 1 < a.rel_hi) {
-      lo++;
-      nxt = __ldg(&a.offsets[lo + 1]);
-    }
-    rel = lo;
-    beg = __ldg(&a.offsets[lo]);
+    beg = __ldg(&a.offsets[rel]);
+    end = __ldg(&a.offsets[rel + 1]);
   }
+  const int i = beg + blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && end - beg > a.n_chunks * a.chunk_beams) *a.error_flag = 1;
+  if (beg + (int)(blockIdx.x * blockDim.x) + (threadIdx.x & ~31) >= end) return; /* whole warp beyond the robot's beams */
+  const bool valid = i < end;
   BeamSeg b;
   b.r0 = b.c0 = b.r1 = b.c1 = b.mr = b.mc = -1;
   if (valid) {
