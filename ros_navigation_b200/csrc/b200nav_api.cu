@@ -1585,6 +1585,17 @@ int b200nav_himm_debug_tile_stats(b200nav_grid* g, int64_t* out2) {
 }
 
 /* Test hook (not part of the drop-in surface): force the coalesced-load window path instead of TMA. */
+#ifdef VFH_STAGE_CLOCKS
+int b200nav_vfh_debug_stage_clocks(unsigned long long* out8, int reset) {
+  if (out8) cudaMemcpyFromSymbol(out8, g_vfh_clk, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_vfh_clk, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 int b200nav_vfh_debug_disable_tma(b200nav_vfh* v, int disable) {
   if (!v) return B200NAV_EINVAL;
   v->tma_disabled = disable != 0;

@@ -67,6 +67,7 @@ struct VfhGridArgs {
 };
 
 #define B200NAV_VFH_THREADS 128
+#define B200NAV_VFH_MAX_SECTORS 384 /* 360 / sector_angle, sector_angle >= 1 */
 #define B200NAV_NRANGES 361
 
 /* ---- reference helper expressions (same promotions as vfh.cpp) ------------------------------------------------ */
@@ -99,10 +100,39 @@ __device__ __forceinline__ float vfh_hypotf(float x, float y) {
   return (float)sqrt((double)x * (double)x + (double)y * (double)y);
 }
 
+/* fmod(fmod(a, p) + p, p) (steerer.cpp:165-168) without the slow fp64 fmod in the common range: fmod is exact, and so
+ * is a - p for p <= a <= 2p (Sterbenz), so both agree bit for bit; anything else (huge or non-finite angles, the sum
+ * rounding up to 2p) takes the library call. */
+__device__ __forceinline__ double vfh_wrap_two_pi(double a, double p) {
+  double m = a;
+  if (!(fabs(a) < p)) {
+    if (fabs(a) < 2.0 * p) m = (a > 0) ? a - p : a + p;
+    else m = fmod(a, p);
+  }
+  const double b = m + p;
+  if (b < p) return b;
+  if (b < 2.0 * p) return b - p;
+  return fmod(b, p);
+}
+
 /* Positive doubles order like their bit patterns: shared-memory atomicMin on the pattern is an exact min. */
 __device__ __forceinline__ void atomic_min_pos_double(double* addr, double v) {
   atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
+
+#ifdef VFH_STAGE_CLOCKS
+__device__ unsigned long long g_vfh_clk[8];
+#define VFH_CLK(k)                                                        \
+  do {                                                                    \
+    if (threadIdx.x == 0) {                                               \
+      const long long now_ = clock64();                                   \
+      atomicAdd(&g_vfh_clk[k], (unsigned long long)(now_ - clk_prev_));   \
+      clk_prev_ = now_;                                                   \
+    }                                                                     \
+  } while (0)
+#else
+#define VFH_CLK(k)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -129,14 +159,26 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
 
   __shared__ SubmapInfo s_sub;
   __shared__ int s_sub_ok;
-  __shared__ int s_warp_cnt[2][B200NAV_VFH_THREADS / 32];
+  __shared__ int s_warp_cnt[4][B200NAV_VFH_THREADS / 32];
   __shared__ float s_red[2][B200NAV_VFH_THREADS / 32];
   __shared__ __align__(8) unsigned long long s_mbar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef VFH_STAGE_CLOCKS
+  long long clk_prev_ = clock64();
+#endif
   const int robot = robot0 + blockIdx.x;
   const b200nav_vfh_input inp = in[blockIdx.x];
   uint32_t flags = 0;
+
+  /* Cant_Turn_To_Goal's goal vector (vfh.cpp:612-654) only depends on the inputs: a lane of the last warp computes it
+   * now (two fp64 sin/cos) instead of the selection thread at the very end of the chain */
+  __shared__ float s_goal[2];
+  __shared__ uint32_t s_blocked[B200NAV_VFH_MAX_SECTORS / 32 + B200NAV_VFH_THREADS / 32]; /* masked histogram == 1 */
+  if (tid == B200NAV_VFH_THREADS - 32) {
+    s_goal[0] = (float)(inp.goal_distance * cos((inp.goal_direction) * 3.14159265358979323846 / 180));
+    s_goal[1] = (float)(inp.goal_distance * sin((inp.goal_direction) * 3.14159265358979323846 / 180));
+  }
 
   /* ================= stage R: pseudo-scan ================= */
   if (FROM_GRID) {
@@ -166,6 +208,7 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
     }
     for (int i = tid; i < B200NAV_NRANGES; i += blockDim.x) s_ranges[i] = 5000.0;
     __syncthreads();
+    VFH_CLK(0); /* submap info + TMA issue */
     const int sub_ok = s_sub_ok;
     if (sub_ok & 1) {
       const SubmapInfo si = s_sub;
@@ -192,40 +235,64 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
       const int ncell = si.size_r * si.size_c;
       const double res = ga.dims.res;
       const double offx = si.pos_x + (0.5 * si.len_x - 0.5 * res), offy = si.pos_y + (0.5 * si.len_y - 0.5 * res);
-      for (int lin = tid; lin < ncell; lin += blockDim.x) {
-        const int i0 = lin % si.size_r, i1 = lin / si.size_r;
-        float value;
-        if (tma) {
-          value = s_window[i1 * ga.box_r + i0 + (si.tl_r & 3)];
-        } else {
-          int b0 = si.utl_r + i0, b1 = si.utl_c + i1;
-          if ((g.start0 | g.start1) != 0) {
-            b0 += g.start0;
-            b1 += g.start1;
-            wrap_index(b0, ga.dims.rows);
-            wrap_index(b1, ga.dims.cols);
+      /* lin -> (i0, i1) = (lin % size_r, lin / size_r) without a division: ncell <= 2^17, size_r <= 2^8 */
+      const unsigned inv_r = si.size_r > 1 ? (unsigned)((0x100000000ull + (unsigned)si.size_r - 1u) / (unsigned)si.size_r) : 0u;
+      constexpr int kBatch = 8; /* window cells in flight per thread: one L2 round trip per batch, not per cell */
+      for (int base = 0; base < ncell; base += kBatch * (int)blockDim.x) {
+        float vals[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+          const int lin = base + u * (int)blockDim.x + tid;
+          vals[u] = __int_as_float(0x7fc00000);
+          if (lin < ncell) {
+            const int i1 = si.size_r > 1 ? (int)__umulhi((unsigned)lin, inv_r) : lin;
+            const int i0 = lin - i1 * si.size_r;
+            if (tma) {
+              vals[u] = s_window[i1 * ga.box_r + i0 + (si.tl_r & 3)];
+            } else {
+              int b0 = si.utl_r + i0, b1 = si.utl_c + i1;
+              if ((g.start0 | g.start1) != 0) {
+                b0 += g.start0;
+                b1 += g.start1;
+                wrap_index(b0, ga.dims.rows);
+                wrap_index(b1, ga.dims.cols);
+              }
+              vals[u] = lay.at(b0, b1);
+            }
           }
-          value = lay.at(b0, b1);
         }
-        if (isnan(value) || value <= c.occupied_threshold) continue;
-        const double px = offx + res * int_to_f64(-i0), py = offy + res * int_to_f64(-i1);
-        const double angle = atan2(py - inp.y, px - inp.x);
-        const double a = angle - inp.yaw + 3.14 / 2;
-        const double twopi = 2.0 * 3.14159265358979323846;
-        const double np = fmod(fmod(a, twopi) + twopi, twopi);
-        const double deg = np * 180.0 / 3.14159265358979323846;
-        if (!(deg <= 180)) continue; /* also rejects NaN poses */
-        const int fl = (int)floor(deg), ce = (int)ceil(deg);
-        const double dx = inp.x - px, dy = inp.y - py;
-        const double distance = sqrt(dx * dx + dy * dy) * 1000.0;
-        atomic_min_pos_double(&s_ranges[fl * 2], distance);
-        atomic_min_pos_double(&s_ranges[ce * 2], distance);
+        /* occupied cells of this thread as a bit set: the expensive fp64 part below then runs once per occupied cell
+         * of the busiest lane, not once per batch slot that is occupied in ANY lane of the warp */
+        unsigned todo = 0u;
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+          if (!(isnan(vals[u]) || vals[u] <= c.occupied_threshold)) todo |= 1u << u;
+        while (todo) {
+          const int u = __ffs(todo) - 1;
+          todo &= todo - 1u;
+          const int lin = base + u * (int)blockDim.x + tid;
+          const int i1 = si.size_r > 1 ? (int)__umulhi((unsigned)lin, inv_r) : lin;
+          const int i0 = lin - i1 * si.size_r;
+          const double px = offx + res * int_to_f64(-i0), py = offy + res * int_to_f64(-i1);
+          const double angle = atan2(py - inp.y, px - inp.x);
+          const double a = angle - inp.yaw + 3.14 / 2;
+          const double twopi = 2.0 * 3.14159265358979323846;
+          const double np = vfh_wrap_two_pi(a, twopi); /* == fmod(fmod(a, twopi) + twopi, twopi), bit for bit */
+          const double deg = np * 180.0 / 3.14159265358979323846;
+          if (!(deg <= 180)) continue; /* also rejects NaN poses */
+          const int fl = (int)floor(deg), ce = (int)ceil(deg);
+          const double dx = inp.x - px, dy = inp.y - py;
+          const double distance = sqrt(dx * dx + dy * dy) * 1000.0;
+          atomic_min_pos_double(&s_ranges[fl * 2], distance);
+          atomic_min_pos_double(&s_ranges[ce * 2], distance);
+        }
       }
     } else {
       flags |= B200NAV_CMD_NO_SUBMAP;
     }
     __syncthreads();
     for (int i = tid; i < B200NAV_NRANGES; i += blockDim.x) v.ranges[(size_t)robot * B200NAV_NRANGES + i] = s_ranges[i];
+    VFH_CLK(1); /* window -> ranges */
   } else {
     for (int i = tid; i < B200NAV_NRANGES; i += blockDim.x) {
       const double r = dev_ranges[(size_t)blockIdx.x * 2 * B200NAV_NRANGES + 2 * i];
@@ -245,31 +312,49 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
   const float r_safe = c.robot_radius + (float)vfh_safety_dist(c, speed);
   int nz_count = 0;
   int emergency_local = 0;
-  for (int f0 = 0, it = 0; f0 < nf; f0 += blockDim.x, it++) {
-    const int f = f0 + tid;
-    bool occ = false;
-    if (f < nf) {
-      const int k = v.kidx[f];
-      if (k >= 0 && v.thr[f] > s_ranges[k]) {
+  /* kSub sub-batches of blockDim cells per pass: their table loads are issued together and one block barrier
+   * orders the whole pass (cell order f is preserved: sub-batch after sub-batch, warp after warp, lane after lane) */
+  constexpr int kSub = 4;
+  for (int f0 = 0; f0 < nf; f0 += kSub * (int)blockDim.x) {
+    int kk[kSub];
+#pragma unroll
+    for (int u = 0; u < kSub; u++) {
+      const int f = f0 + u * (int)blockDim.x + tid;
+      kk[u] = (f < nf) ? (int)v.kidx[f] : -1;
+    }
+    unsigned bal[kSub];
+    bool occ[kSub];
+#pragma unroll
+    for (int u = 0; u < kSub; u++) {
+      const int f = f0 + u * (int)blockDim.x + tid;
+      occ[u] = false;
+      if (kk[u] >= 0 && v.thr[f] > s_ranges[kk[u]]) {
         const int x = f % W, y = f / W;
         if (v.dist[f] < r_safe && !(x == c.center && y == c.center)) emergency_local = 1;
-        occ = true;
+        occ[u] = true;
       }
+      bal[u] = __ballot_sync(0xffffffffu, occ[u]);
+      if (lane == 0) s_warp_cnt[u][warp] = __popc(bal[u]);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, occ);
-    if (lane == 0) s_warp_cnt[it & 1][warp] = __popc(bal);
     __syncthreads();
-    int pos = nz_count, tot = 0;
+    int base_pos = nz_count;
 #pragma unroll
-    for (int w = 0; w < B200NAV_VFH_THREADS / 32; w++) {
-      const int cw = s_warp_cnt[it & 1][w];
-      if (w < warp) pos += cw;
-      tot += cw;
+    for (int u = 0; u < kSub; u++) {
+      int pos = base_pos, tot = 0;
+#pragma unroll
+      for (int w = 0; w < B200NAV_VFH_THREADS / 32; w++) {
+        const int cw = s_warp_cnt[u][w];
+        if (w < warp) pos += cw;
+        tot += cw;
+      }
+      if (occ[u]) s_nz[pos + __popc(bal[u] & ((1u << lane) - 1u))] = (uint16_t)(f0 + u * (int)blockDim.x + tid);
+      base_pos += tot;
     }
-    if (occ) s_nz[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)f;
-    nz_count += tot;
+    nz_count = base_pos;
+    __syncthreads(); /* s_warp_cnt is rewritten by the next pass */
   }
   const int emergency = __syncthreads_or(emergency_local);
+  VFH_CLK(2); /* stage M */
 
   float* g_origin = v.origin_hist + (size_t)robot * H;
   float* g_hist = v.hist + (size_t)robot * H;
@@ -289,7 +374,23 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
       float h = 0.f;
       const int word = s >> 5;
       const uint32_t bit = 1u << (s & 31);
-      for (int j = 0; j < nz_count; j++) {
+      /* occupied cells in (y outer, x inner) order; the table loads of four cells are in flight together, the sum
+       * keeps the reference's order */
+      int j = 0;
+      for (; j + 4 <= nz_count; j += 4) {
+        uint32_t mw[4];
+        float bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int f = s_nz[j + u];
+          mw[u] = __ldg(&masks[(size_t)f * c.nwords + word]);
+          bv[u] = __ldg(&v.base[f]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (mw[u] & bit) h += bv[u];
+      }
+      for (; j < nz_count; j++) {
         const int f = s_nz[j];
         if (__ldg(&masks[(size_t)f * c.nwords + word]) & bit) h += __ldg(&v.base[f]);
       }
@@ -333,25 +434,28 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
       s_red[1][warp] = pl;
     }
     __syncthreads(); /* also publishes s_hist */
+    VFH_CLK(3); /* stages H, B, K */
 #pragma unroll
     for (int w = 0; w < B200NAV_VFH_THREADS / 32; w++) {
       phi_right = fmaxf(phi_right, s_red[0][w]);
       phi_left = fminf(phi_left, s_red[1][w]);
     }
-    /* mask (vfh.cpp:1196-1210) */
-    for (int s = tid; s < H; s += blockDim.x) {
-      const float angle = (float)(s * c.sector_angle);
-      float m;
-      if ((s_hist[s] == 0) &&
-          (((vfh_delta_angle(angle, phi_right) <= 0) && (vfh_delta_angle(angle, 90.f) >= 0)) ||
-           ((vfh_delta_angle(angle, phi_left) >= 0) && (vfh_delta_angle(angle, 90.f) <= 0))))
-        m = 0.f;
-      else
-        m = 1.f;
-      s_hist[s] = m;
-      g_hist[s] = m;
+    /* mask (vfh.cpp:1196-1210); the blocked sectors also go into a bit set for the selection stage */
+    for (int s0 = 0; s0 < H; s0 += blockDim.x) {
+      const int s = s0 + tid;
+      bool blocked = false;
+      if (s < H) {
+        const float angle = (float)(s * c.sector_angle);
+        blocked = !((s_hist[s] == 0) &&
+                    (((vfh_delta_angle(angle, phi_right) <= 0) && (vfh_delta_angle(angle, 90.f) >= 0)) ||
+                     ((vfh_delta_angle(angle, phi_left) >= 0) && (vfh_delta_angle(angle, 90.f) <= 0))));
+        g_hist[s] = blocked ? 1.f : 0.f;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, blocked);
+      if (lane == 0) s_blocked[(s0 >> 5) + warp] = bal;
     }
     __syncthreads();
+    VFH_CLK(4); /* mask */
   }
 
   /* ================= stage S: direction, speed, turn rate (single thread) ================= */
@@ -361,9 +465,10 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
       st.max_speed_for_picked = 0;
       st.last_picked = st.picked;
     } else {
+      auto is_blocked = [&](int s) { return (s_blocked[s >> 5] >> (s & 31)) & 1u; };
       int start = -1;
       for (int i = 0; i < H / 2; i++)
-        if (s_hist[i] == 1) {
+        if (is_blocked(i)) {
           start = i;
           break;
         }
@@ -389,32 +494,59 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
         const int cmax = c.current_max_speed;
         const int sp_narrow = (cmax < c.max_speed_narrow) ? cmax : c.max_speed_narrow;
         const int sp_wide = (cmax < c.max_speed_wide) ? cmax : c.max_speed_wide;
-        int left = 1, first = 0, second = 0;
-        for (int i = start; i <= start + H; i++) {
-          const int s = i % H;
-          if ((s_hist[s] == 0) && left) {
-            first = s * c.sector_angle;
-            left = 0;
+        /* The reference walks the H + 1 positions n = 0..H, sector s(n) = (start + n) % H, and toggles between
+         * "looking for a free sector" (-> first) and "looking for a blocked one" (-> second), vfh.cpp:786-868.  Only
+         * those events matter, so they are found with bit scans over the blocked-sector set instead of visiting every
+         * position.  s(0) = s(H) = start is blocked, so every opening is closed by n = H at the latest. */
+        auto find = [&](int lo, int hi, bool want) -> int { /* first s in [lo, hi) with blocked == want, else -1 */
+          while (lo < hi) {
+            const int w = lo >> 5, lim = min(hi, (w + 1) << 5);
+            uint32_t bits = want ? s_blocked[w] : ~s_blocked[w];
+            bits &= 0xffffffffu << (lo & 31);
+            if (lim - (w << 5) < 32) bits &= (1u << (lim - (w << 5))) - 1u;
+            if (bits) return (w << 5) + __ffs(bits) - 1;
+            lo = lim;
           }
-          if ((s_hist[s] == 1) && !left) {
-            second = (s - 1) * c.sector_angle;
-            if (second < 0) second += 360;
-            left = 1;
-            const float angle = vfh_delta_angle((float)first, (float)second);
-            if (fabsf(angle) < 10) continue;
-            const float centre = (float)(first + (second - first) / 2.0);
-            if (fabsf(angle) < 80) {
-              consider(centre, sp_narrow);
-            } else {
-              consider(centre, cmax);
-              const float c2 = (float)((first + 40) % 360);
-              consider(c2, sp_wide);
-              float c3 = (float)(second - 40);
-              if (c3 < 0) c3 += 360;
-              consider(c3, sp_wide);
-              if ((vfh_delta_angle(st.desired, c2) < 0) && (vfh_delta_angle(st.desired, c3) > 0))
-                consider(st.desired, sp_wide);
-            }
+          return -1;
+        };
+        const int wrap_at = H - start; /* positions n >= wrap_at map to s = n - wrap_at */
+        auto next_event = [&](int n, bool want) -> int { /* first n' in [n, H] with blocked(s(n')) == want, else H+1 */
+          if (n < wrap_at) {
+            const int s = find(start + n, H, want);
+            if (s >= 0) return s - start;
+            n = wrap_at;
+          }
+          if (n <= H) {
+            const int s = find(n - wrap_at, start + 1, want);
+            if (s >= 0) return s + wrap_at;
+          }
+          return H + 1;
+        };
+        int first = 0, second = 0;
+        for (int n = 0;;) {
+          n = next_event(n, false); /* free sector while looking left */
+          if (n > H) break;
+          first = ((n < wrap_at) ? start + n : n - wrap_at) * c.sector_angle;
+          n = next_event(n + 1, true); /* the blocked sector that closes the opening */
+          if (n > H) break;
+          const int s = (n < wrap_at) ? start + n : n - wrap_at;
+          n++;
+          second = (s - 1) * c.sector_angle;
+          if (second < 0) second += 360;
+          const float angle = vfh_delta_angle((float)first, (float)second);
+          if (fabsf(angle) < 10) continue;
+          const float centre = (float)(first + (second - first) / 2.0);
+          if (fabsf(angle) < 80) {
+            consider(centre, sp_narrow);
+          } else {
+            consider(centre, cmax);
+            const float c2 = (float)((first + 40) % 360);
+            consider(c2, sp_wide);
+            float c3 = (float)(second - 40);
+            if (c3 < 0) c3 += 360;
+            consider(c3, sp_wide);
+            if ((vfh_delta_angle(st.desired, c2) < 0) && (vfh_delta_angle(st.desired, c3) > 0))
+              consider(st.desired, sp_wide);
           }
         }
         if (n_cand == 0) {
@@ -435,8 +567,7 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
     else speed_incr = (int)(c.max_acceleration * inp.dt);
     {
       /* Cant_Turn_To_Goal (vfh.cpp:612-654) */
-      const float goal_x = (float)(inp.goal_distance * cos((st.desired) * 3.14159265358979323846 / 180));
-      const float goal_y = (float)(inp.goal_distance * sin((st.desired) * 3.14159265358979323846 / 180));
+      const float goal_x = s_goal[0], goal_y = s_goal[1]; /* st.desired == inp.goal_direction */
       const float rb = st.blocked_radius;
       bool cant = false;
       float dc = vfh_hypotf(goal_x - rb, goal_y);
@@ -477,6 +608,7 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
     cmd.picked_angle = st.picked;
     cmd.flags = flags;
     out[blockIdx.x] = cmd;
+    VFH_CLK(5); /* stage S */
   }
 }
 
