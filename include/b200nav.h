@@ -174,6 +174,32 @@ int b200nav_himm_update_cloud_batched(b200nav_grid* grid, const char* layer, con
 int b200nav_himm_update_cloud_batched_async(b200nav_grid* grid, const char* layer, const double* host_origins,
                                             const float* host_xy, const uint8_t* host_clear_end,
                                             const int32_t* host_offsets);
+/* ------------------------------------------------------------------------------------------------------
+ * Scan form: raw LaserScans + the sensor pose, projected on the device.  Replaces the intake side of
+ * LaserMapUpdater::bufferIncomingMsg (move_control/src/laser_map_updater.cpp:38-144: getLaserOriginOnGlobal,
+ * simplifyLaserScan, laser_geometry's projection, the RangeSample loop).  laser_geometry / tf are not part of the
+ * reference tree; their arithmetic is restated as an explicit specification in
+ * ros_navigation_b200/csrc/scan_project.h (parity with the reference unpinned there, bit-exact with oracle/).
+ *   info:   the LaserScan header fields shared by all robots; decimate != 0 applies simplifyLaserScan (the
+ *           reference always does: scans finer than 0.017 rad are thinned to about one reading per degree)
+ *   poses:  n_robots * 3 doubles: sensor x, y, yaw in the map frame at the scan's stamp
+ *   ranges: n_robots * n_ranges floats
+ * 4 bytes per reading cross PCIe instead of the 40-byte RangeSample.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct b200nav_scan_info {
+  float angle_min, angle_increment, range_min, range_max;
+  int32_t n_ranges;
+  int32_t decimate;
+} b200nav_scan_info;
+/* simplifyLaserScan: indices of the readings that are projected (sel may be NULL) and the angle increment the
+ * projection uses; returns their number. */
+int b200nav_scan_select(const b200nav_scan_info* info, int32_t* sel, int cap, float* increment_used);
+int b200nav_himm_update_scans_batched(b200nav_grid* grid, const char* layer, const b200nav_scan_info* info,
+                                      const double* host_poses, const float* host_ranges);
+/* Same with device arrays; asynchronous. */
+int b200nav_himm_update_scans_batched_dev(b200nav_grid* grid, const char* layer, const b200nav_scan_info* info,
+                                          const double* dev_poses, const float* dev_ranges);
+
 int b200nav_himm_update_cloud_batched_dev(b200nav_grid* grid, const char* layer, const double* dev_origins,
                                           const float* dev_xy, const uint8_t* dev_clear_end,
                                           const int32_t* dev_offsets, int total, int max_samples_per_robot);

@@ -579,4 +579,88 @@ void oracle_goal_from_pose(double rx, double ry, double yaw, double tx, double t
   *desired_angle = static_cast<float>(np * 180.0 / M_PI);
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * LaserScan -> RangeSamples (intake side of LaserMapUpdater::bufferIncomingMsg, laser_map_updater.cpp:38-144).
+ * laser_geometry and tf are not in the reference tree, so this restates the SPECIFICATION written down in
+ * ros_navigation_b200/csrc/scan_project.h (an independent implementation of the same arithmetic, operation by
+ * operation) - parity with the reference is unpinned at this boundary.
+ * ------------------------------------------------------------------------------------------------------------- */
+void oracle_sincos(double x, double* s_out, double* c_out) {
+  /* reduction: n = nearest integer to x * 2/pi, r = x - n * pi/2 with pi/2 split into three 33-bit pieces */
+  static const double kInvPio2 = 6.36619772367581382433e-01;
+  static const double kPio2[3] = {1.57079632673412561417e+00, 6.07710050630396597660e-11, 2.02226624871116645580e-21};
+  static const double kS[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                               2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+  static const double kC[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                               -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+  volatile double t = x * kInvPio2 + 6755399441055744.0; /* round to nearest integer (ties to even) */
+  const double fn = t - 6755399441055744.0;
+  double r = x - fn * kPio2[0];
+  r = r - fn * kPio2[1];
+  r = r - fn * kPio2[2];
+  const double z = r * r;
+  double ps = kS[5];
+  for (int i = 4; i >= 0; i--) ps = kS[i] + z * ps; /* Horner, innermost coefficient first */
+  double pc = kC[5];
+  for (int i = 4; i >= 0; i--) pc = kC[i] + z * pc;
+  const double sin_r = r + r * (z * ps);
+  const double cos_r = 1.0 - (0.5 * z - (z * z) * pc);
+  const long long n = static_cast<long long>(fn);
+  switch (static_cast<int>(n & 3)) {
+    case 0: *s_out = sin_r; *c_out = cos_r; break;
+    case 1: *s_out = cos_r; *c_out = -sin_r; break;
+    case 2: *s_out = -sin_r; *c_out = -cos_r; break;
+    default: *s_out = -cos_r; *c_out = sin_r; break;
+  }
+}
+
+int oracle_scan_select(float angle_increment, int n_ranges, int decimate, int* sel, float* increment_used) {
+  /* simplifyLaserScan (laser_map_updater.cpp:114-144) is applied when angle_increment < 0.017 (:74) */
+  int n = 0;
+  *increment_used = angle_increment;
+  if (decimate && angle_increment < 0.017 && n_ranges > 0) {
+    sel[n++] = 0; /* convertedLaserScan.ranges.push_back(msg->ranges[0]) */
+    float increment = 0.0;
+    for (int i = 0; i < n_ranges; i++) {
+      increment += angle_increment;
+      if (increment >= 0.017) {
+        *increment_used = increment;
+        increment = 0.0;
+        sel[n++] = i;
+      }
+    }
+    return n;
+  }
+  for (int i = 0; i < n_ranges; i++) sel[n++] = i;
+  return n;
+}
+
+int oracle_project_scan(float angle_min, float increment_used, float range_min, float range_max, const int* sel,
+                        int n_used, const float* ranges, double x0, double y0, double yaw, oracle_sample* out) {
+  double sin_yaw, cos_yaw;
+  oracle_sincos(yaw, &sin_yaw, &cos_yaw);
+  int n = 0;
+  for (int j = 0; j < n_used; j++) {
+    const float range = ranges[sel[j]];
+    if (!(range < range_max && range >= range_min)) continue; /* laser_geometry keeps range_min <= r < range_max */
+    const double angle = static_cast<double>(angle_min) + static_cast<double>(j) * static_cast<double>(increment_used);
+    double sa, ca;
+    oracle_sincos(angle, &sa, &ca);
+    /* point in the sensor frame, stored as float32 in the cloud */
+    const float local_x = static_cast<float>(static_cast<double>(range) * ca);
+    const float local_y = static_cast<float>(static_cast<double>(range) * sa);
+    /* rigid transform into the map frame in double, stored back as float32 */
+    const float map_x = static_cast<float>((cos_yaw * local_x - sin_yaw * local_y) + x0);
+    const float map_y = static_cast<float>((sin_yaw * local_x + cos_yaw * local_y) + y0);
+    out[n].sx = x0; /* getLaserOriginOnGlobal */
+    out[n].sy = y0;
+    out[n].ex = map_x; /* Position(*itX, *itY) */
+    out[n].ey = map_y;
+    out[n].clear_end = 0;
+    out[n].pad_ = 0;
+    n++;
+  }
+  return n;
+}
+
 } /* extern "C" */

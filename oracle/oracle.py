@@ -69,6 +69,9 @@ def lib():
         L.oracle_to_occupancy.argtypes = [gp, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         L.oracle_goal_from_pose.argtypes = [C.c_double] * 5 + [_fp, _fp]
         L.oracle_if_blocked.argtypes = [gp, C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.oracle_sincos.argtypes = [C.c_double, _dp, _dp]
+        L.oracle_scan_select.argtypes = [C.c_float, C.c_int, C.c_int, C.c_void_p, _fp]
+        L.oracle_project_scan.argtypes = [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p] + [C.c_double] * 3 + [C.c_void_p]
         _lib = L
     return _lib
 
@@ -193,6 +196,32 @@ def ranges_from_submap(g, master, rx, ry, yaw, submap_len=1.5):
     ranges = np.zeros((361, 2), dtype=np.float64)
     lib().oracle_ranges_from_submap(C.byref(g), master.ctypes.data, rx, ry, yaw, submap_len, ranges.ctypes.data)
     return ranges
+
+
+def sincos(x):
+    s, c = C.c_double(), C.c_double()
+    lib().oracle_sincos(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def scan_select(angle_increment, n_ranges, decimate=True):
+    """simplifyLaserScan: (indices of the projected readings, angle increment the projection uses)."""
+    sel = np.zeros(n_ranges + 1, np.int32)
+    used = C.c_float()
+    n = lib().oracle_scan_select(float(angle_increment), int(n_ranges), int(bool(decimate)), sel.ctypes.data,
+                                 C.byref(used))
+    return sel[:n].copy(), used.value
+
+
+def project_scan(angle_min, angle_increment, range_min, range_max, ranges, pose, decimate=True):
+    """RangeSamples of one LaserScan taken at sensor pose (x, y, yaw) in the map frame (spec: scan_project.h)."""
+    ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+    sel, used = scan_select(np.float32(angle_increment), len(ranges), decimate)
+    out = np.zeros(len(sel), dtype=SAMPLE_DTYPE)
+    n = lib().oracle_project_scan(float(np.float32(angle_min)), used, float(np.float32(range_min)),
+                                  float(np.float32(range_max)), sel.ctypes.data, len(sel), ranges.ctypes.data,
+                                  float(pose[0]), float(pose[1]), float(pose[2]), out.ctypes.data)
+    return out[:n].copy()
 
 
 def move(g, layers, x, y):

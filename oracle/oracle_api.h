@@ -94,6 +94,16 @@ int oracle_if_blocked(const oracle_geom* g, const float* master, double x, doubl
 void oracle_goal_from_pose(double rx, double ry, double yaw, double tx, double ty,
                            float* desired_angle, float* desired_dist);
 
+/* LaserScan -> RangeSamples: restatement of the specification in ros_navigation_b200/csrc/scan_project.h (intake side
+ * of LaserMapUpdater::bufferIncomingMsg, laser_map_updater.cpp:38-144; laser_geometry / tf are not in the reference
+ * tree: parity with the reference unpinned here). */
+void oracle_sincos(double x, double* s, double* c);
+/* simplifyLaserScan (laser_map_updater.cpp:114-144): sel[] = projected range indices (cap n_ranges + 1); returns n. */
+int oracle_scan_select(float angle_increment, int n_ranges, int decimate, int* sel, float* increment_used);
+/* Samples of one scan taken at sensor pose (x0, y0, yaw); dropped readings are skipped.  Returns the sample count. */
+int oracle_project_scan(float angle_min, float increment_used, float range_min, float range_max, const int* sel,
+                        int n_used, const float* ranges, double x0, double y0, double yaw, oracle_sample* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,8 @@ SAMPLE_DTYPE = np.dtype([("sx", "<f8"), ("sy", "<f8"), ("ex", "<f8"), ("ey", "<f
                          ("reserved", "<i4")])
 VFH_INPUT_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("yaw", "<f8"), ("dt", "<f8"), ("current_speed", "<i4"),
                             ("goal_direction", "<f4"), ("goal_distance", "<f4"), ("goal_tolerance", "<f4")])
+SCAN_INFO_DTYPE = np.dtype([("angle_min", "<f4"), ("angle_increment", "<f4"), ("range_min", "<f4"),
+                            ("range_max", "<f4"), ("n_ranges", "<i4"), ("decimate", "<i4")])
 COMMAND_DTYPE = np.dtype([("speed", "<i4"), ("turnrate", "<i4"), ("picked_angle", "<f4"), ("flags", "<u4")])
 assert SAMPLE_DTYPE.itemsize == 40 and VFH_INPUT_DTYPE.itemsize == 48 and COMMAND_DTYPE.itemsize == 16
 
@@ -73,6 +75,9 @@ _SIGNATURES = {
     "b200nav_himm_update_cloud_batched_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                           C.c_void_p]),
     "b200nav_vfh_update_batched_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
+    "b200nav_scan_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "b200nav_himm_update_scans_batched": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200nav_himm_update_scans_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200nav_grid_has_layer": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_grid_layer_format": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_update": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -132,6 +132,12 @@ struct b200nav_grid {
   cudaEvent_t tile_done[2] = {nullptr, nullptr};
   bool tile_done_set[2] = {false, false};
   int cloud_slot = 0;
+  /* scan form: cached selection / regular offsets for the last b200nav_scan_info, staging of poses and ranges */
+  DevBuf scan_sel, scan_offsets, scan_poses, scan_ranges;
+  b200nav_scan_info scan_info_cached = b200nav_scan_info();
+  bool scan_cache_valid = false;
+  int scan_n_used = 0;
+  float scan_increment_used = 0.f;
   DevBuf stage, convflag; /* float staging for upload / download of CODED layers; conversion "bad value" flag */
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
@@ -349,6 +355,11 @@ struct CloudIn {
   const double* origins = nullptr;
   const float* xy = nullptr;
   const uint8_t* clear_end = nullptr;
+  /* scan form */
+  const float* scan_ranges = nullptr;
+  const double* scan_poses = nullptr;
+  const int32_t* scan_sel = nullptr;
+  ScanModel scan = ScanModel();
 };
 
 int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, const int32_t* dev_offsets,
@@ -364,6 +375,10 @@ int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, c
   a.origins = cloud.origins;
   a.xy = reinterpret_cast<const float2*>(cloud.xy);
   a.clear_end = cloud.clear_end;
+  a.scan_ranges = cloud.scan_ranges;
+  a.scan_poses = cloud.scan_poses;
+  a.scan_sel = cloud.scan_sel;
+  a.scan = cloud.scan;
   a.offsets = dev_offsets;
   a.segs = static_cast<BeamSeg*>(g->segs.p);
   a.robot0 = robot0;
@@ -749,6 +764,10 @@ int b200nav_grid_destroy(b200nav_grid* g) {
   g->layers.clear(); /* frees the device buffers */
   g->stage.release();
   g->convflag.release();
+  g->scan_sel.release();
+  g->scan_offsets.release();
+  g->scan_poses.release();
+  g->scan_ranges.release();
   for (int i = 0; i < 2; i++) {
     g->offs2[i].release();
     g->orig2[i].release();
@@ -1265,6 +1284,100 @@ int b200nav_himm_update_cloud_batched_dev(b200nav_grid* g, const char* layer, co
   c.xy = dev_xy;
   c.clear_end = dev_clear_end;
   return himm_launch(g, l, nullptr, dev_offsets, 0, g->n_robots, -1, total, max_samples_per_robot, c);
+}
+
+/* simplifyLaserScan (laser_map_updater.cpp:114-144) restated: which ranges of a scan are projected and with which
+ * angle increment.  Returns the number of selected ranges (sel may be NULL to only count). */
+int b200nav_scan_select(const b200nav_scan_info* info, int32_t* sel, int cap, float* increment_used) {
+  if (!info || info->n_ranges < 0) return B200NAV_EINVAL;
+  int n = 0;
+  float used = info->angle_increment;
+  if (info->decimate && info->angle_increment < 0.017f && info->n_ranges > 0) {
+    /* ranges[0] first, then every index at which the float accumulator reaches 0.017 (the comparison is made in
+     * double, as `increment >= 0.017` promotes the float) */
+    if (sel && n < cap) sel[n] = 0;
+    n++;
+    float increment = 0.0f;
+    for (int i = 0; i < info->n_ranges; i++) {
+      increment += info->angle_increment;
+      if ((double)increment >= 0.017) {
+        used = increment;
+        increment = 0.0f;
+        if (sel && n < cap) sel[n] = i;
+        n++;
+      }
+    }
+  } else {
+    for (int i = 0; i < info->n_ranges; i++) {
+      if (sel && n < cap) sel[n] = i;
+      n++;
+    }
+  }
+  if (increment_used) *increment_used = used;
+  return n;
+}
+
+static int himm_update_scans(b200nav_grid* g, const char* layer, const b200nav_scan_info* info, const double* poses,
+                             const float* ranges, bool host) {
+  if (!g || !info || !poses || !ranges || info->n_ranges <= 0) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  b200nav_ctx* ctx = g->ctx;
+  const int nr = g->n_robots;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!g->scan_cache_valid || memcmp(&g->scan_info_cached, info, sizeof(*info)) != 0) {
+    std::vector<int32_t> sel((size_t)info->n_ranges + 1);
+    float used = 0.f;
+    const int n_used = b200nav_scan_select(info, sel.data(), (int)sel.size(), &used);
+    if (n_used < 0) return n_used;
+    if ((long long)n_used * nr > 0x7fffffffLL) return set_err(ctx, B200NAV_ERANGE, "too many samples for one update");
+    std::vector<int32_t> offs((size_t)nr + 1);
+    for (int r = 0; r <= nr; r++) offs[r] = r * n_used;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); /* an earlier update may still read the cached arrays */
+    CUDA_TRY(ctx, g->scan_sel.reserve(sizeof(int32_t) * (size_t)std::max(n_used, 1)));
+    CUDA_TRY(ctx, g->scan_offsets.reserve(sizeof(int32_t) * ((size_t)nr + 1)));
+    CUDA_TRY(ctx, cudaMemcpy(g->scan_sel.p, sel.data(), sizeof(int32_t) * (size_t)n_used, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->scan_offsets.p, offs.data(), sizeof(int32_t) * offs.size(), cudaMemcpyHostToDevice));
+    g->scan_info_cached = *info;
+    g->scan_n_used = n_used;
+    g->scan_increment_used = used;
+    g->scan_cache_valid = true;
+  }
+  const int n_used = g->scan_n_used;
+  if (n_used == 0) return B200NAV_OK;
+  CloudIn c;
+  if (host) {
+    CUDA_TRY(ctx, g->scan_poses.reserve(sizeof(double) * 3 * (size_t)nr));
+    CUDA_TRY(ctx, g->scan_ranges.reserve(sizeof(float) * (size_t)nr * info->n_ranges));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g->scan_poses.p, poses, sizeof(double) * 3 * (size_t)nr, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g->scan_ranges.p, ranges, sizeof(float) * (size_t)nr * info->n_ranges,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    c.scan_poses = static_cast<const double*>(g->scan_poses.p);
+    c.scan_ranges = static_cast<const float*>(g->scan_ranges.p);
+  } else {
+    c.scan_poses = poses;
+    c.scan_ranges = ranges;
+  }
+  c.scan_sel = (n_used == info->n_ranges) ? nullptr : static_cast<const int32_t*>(g->scan_sel.p);
+  c.scan.angle_min = info->angle_min;
+  c.scan.increment_used = g->scan_increment_used;
+  c.scan.range_min = info->range_min;
+  c.scan.range_max = info->range_max;
+  c.scan.n_ranges = info->n_ranges;
+  c.scan.n_used = n_used;
+  int rc = himm_launch(g, l, nullptr, static_cast<const int32_t*>(g->scan_offsets.p), 0, nr, -1, nr * n_used, n_used, c);
+  if (rc) return rc;
+  return host ? sync_stream(ctx) : B200NAV_OK;
+}
+
+int b200nav_himm_update_scans_batched(b200nav_grid* g, const char* layer, const b200nav_scan_info* info,
+                                      const double* host_poses, const float* host_ranges) {
+  return himm_update_scans(g, layer, info, host_poses, host_ranges, true);
+}
+
+int b200nav_himm_update_scans_batched_dev(b200nav_grid* g, const char* layer, const b200nav_scan_info* info,
+                                          const double* dev_poses, const float* dev_ranges) {
+  return himm_update_scans(g, layer, info, dev_poses, dev_ranges, false);
 }
 
 int b200nav_himm_last_stats(b200nav_grid* g, int64_t* out3) {

@@ -27,6 +27,7 @@
 #include "../../include/b200nav.h"
 #include "cells.cuh"
 #include "geometry.h"
+#include "scan_project.h"
 
 namespace b200nav {
 
@@ -42,6 +43,11 @@ struct HimmArgs {
   const double* origins;          /* cloud form: [n_active][2] laser origin per robot  */
   const float2* xy;               /* cloud form: [total] float32 end points            */
   const uint8_t* clear_end;       /* cloud form: [total] ifClearEnd flags or NULL      */
+  /* scan form (scan_project.h): raw ranges + sensor pose per robot; the binning kernel projects them itself */
+  const float* scan_ranges;       /* [n_active][scan.n_ranges] or NULL                 */
+  const double* scan_poses;       /* [n_active][3] sensor x, y, yaw in the map frame   */
+  const int32_t* scan_sel;        /* [scan.n_used] selected range indices or NULL (identity) */
+  ScanModel scan;
   const int32_t* offsets;         /* device [n_robots+1], or NULL in single mode  */
   BeamSeg* segs;                  /* device scratch [total]                       */
   /* binning scratch, all-zero between updates (the tile kernel clears what it consumes):
@@ -116,6 +122,17 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
       ex = s.ex;
       ey = s.ey;
       clear_end = s.clear_end;
+    } else if (a.scan_ranges) { /* scan form: project the reading (scan_project.h); dropped readings do nothing */
+      const double* pose = a.scan_poses + 3 * (size_t)rel;
+      sx = pose[0];
+      sy = pose[1];
+      double syaw, cyaw;
+      b200nav_sincos(pose[2], syaw, cyaw);
+      const int j = i - beg;
+      const int src = a.scan_sel ? __ldg(&a.scan_sel[j]) : j;
+      const float r = __ldg(&a.scan_ranges[(size_t)rel * a.scan.n_ranges + src]);
+      clear_end = 0;
+      if (!project_reading(a.scan, j, r, sx, sy, cyaw, syaw, ex, ey)) ex = ey = __longlong_as_double(0x7ff8000000000000ll);
     } else { /* cloud form: Position(*itX, *itY) widens the float32 cloud point (laser_map_updater.cpp:60) */
       const float2 p = a.xy[i];
       sx = a.origins[2 * rel];

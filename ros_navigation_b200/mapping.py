@@ -123,6 +123,28 @@ class DeviceGridMap:
                                                       None if ce is None else ce.ctypes.data, offsets.ctypes.data,
                                                       ptr(bbox)), self.ctx.h)
 
+    @staticmethod
+    def scan_info(angle_min, angle_increment, range_min, range_max, n_ranges, decimate=True):
+        from .capi import SCAN_INFO_DTYPE
+        info = np.zeros(1, SCAN_INFO_DTYPE)
+        info["angle_min"], info["angle_increment"] = angle_min, angle_increment
+        info["range_min"], info["range_max"] = range_min, range_max
+        info["n_ranges"], info["decimate"] = n_ranges, int(bool(decimate))
+        return info
+
+    def himm_update_scans_batched(self, layer, info, poses, ranges):
+        """Scan form (b200nav_himm_update_scans_batched): poses [n_robots,3] f64 sensor x, y, yaw; ranges
+        [n_robots, n_ranges] f32; the projection runs inside the binning kernel."""
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        ranges = np.ascontiguousarray(ranges, dtype=np.float32)
+        assert poses.shape == (self.n_robots, 3) and ranges.shape == (self.n_robots, int(info["n_ranges"][0]))
+        check(lib().b200nav_himm_update_scans_batched(self.h, layer.encode(), info.ctypes.data, poses.ctypes.data,
+                                                      ranges.ctypes.data), self.ctx.h)
+
+    def himm_update_scans_batched_dev(self, layer, info, dev_poses, dev_ranges):
+        check(lib().b200nav_himm_update_scans_batched_dev(self.h, layer.encode(), info.ctypes.data, ptr(dev_poses),
+                                                          ptr(dev_ranges)), self.ctx.h)
+
     def himm_update_cloud_batched_async(self, layer, origins, xy, clear_end, offsets):
         """Enqueue-only form: the arguments must be host buffers (pinned torch tensors / numpy arrays) that stay valid
         and unchanged until the context has caught up (Context.wait / synchronize)."""
