@@ -491,6 +491,20 @@ def run_gpu_arm(args, rank, world, local_rank):
                                "vfh_update": vfh_ms / max(vfh_n, 1)},
         "wall_s_timed_region": wall,
     }
+    # the two smaller kernels against the same HBM peak (SURVEY section 8d accounting; both are latency bound)
+    beams = float(np.mean([u[3] for u in used]))
+    n_sub = int(math.ceil(arm.cfg["submap"] / arm.cfg["res"])) + 1
+    prep_avg, vfh_avg = prep_ms / max(prep_n, 1), vfh_ms / max(vfh_n, 1)
+    prep_bytes = beams * (9 + 24)               # cloud point in (8 B xy + 1 B flag) + 24 B BeamSeg out
+    vfh_bytes = arm.n * (4 * n_sub * n_sub + 2888 + 3 * 288 + 16)
+    line["roofline_other"] = {
+        "himm_prep_kernel": {"bytes_per_launch": prep_bytes, "achieved": prep_bytes / (prep_avg / 1e3) / 1e9,
+                             "frac": prep_bytes / (prep_avg / 1e3) / 1e9 / hbm_peak, "unit": "GB/s",
+                             "note": "instruction / latency bound (fp64 clipping, warp-aggregated RED.OR binning)"},
+        "vfh_update_kernel": {"bytes_per_launch": vfh_bytes, "achieved": vfh_bytes / (vfh_avg / 1e3) / 1e9,
+                              "frac": vfh_bytes / (vfh_avg / 1e3) / 1e9 / hbm_peak, "unit": "GB/s",
+                              "note": "latency bound: one 128-thread CTA per robot, %.2f waves" % (arm.n / (148.0 * 8))},
+    }
     # ---- CPU baseline on a bounded sample (rank 0, N == 1 only) ----
     if world == 1 and not args.no_cpu:
         try:

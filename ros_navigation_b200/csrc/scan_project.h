@@ -6,7 +6,7 @@
  * laser_geometry::LaserProjection::transformLaserScanToPointCloud and the per-point loop that fills RangeSamples.
  * laser_geometry and tf are third-party code that is NOT in the reference tree (ROS indigo, un-vendored), so their
  * arithmetic is restated here as an explicit specification - parity with the reference is UNPINNED at this boundary
- * (SURVEY section 8c); parity with oracle/ (an independent restatement of this same specification) is bit-exact:
+ * (SURVEY section 8c); parity with the test suite's independent CPU restatement of this same specification is bit-exact:
  *
  *   selection   simplifyLaserScan (laser_map_updater.cpp:126-144): if angle_increment < 0.017 keep ranges[0] and then
  *               every ranges[i] at which the float accumulator `increment += angle_increment` reaches 0.017 (reset to
@@ -20,8 +20,8 @@
  *   sample      start = (x0, y0) (getLaserOriginOnGlobal), end = ((double)X, (double)Y), ifClearEnd = false (readings
  *               at or beyond range_max never reach the loop, laser_map_updater.cpp:62-66).
  *   sin / cos   b200nav_sincos below: a fixed sequence of individually rounded fp64 operations (Cody-Waite reduction
- *               by pi/2 in three 33-bit pieces, the classic degree-13 / degree-14 minimax kernels), so that the CPU
- *               oracle and the GPU produce the same bits.  |x| < 2^20 * pi/2; about 1 ulp.
+ *               by pi/2 in three 33-bit pieces, the classic degree-13 / degree-14 minimax kernels), so that a CPU
+ *               restatement and the GPU produce the same bits.  |x| < 2^20 * pi/2; about 1 ulp.
  */
 #ifndef B200NAV_SCAN_PROJECT_H
 #define B200NAV_SCAN_PROJECT_H
