@@ -221,7 +221,7 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "u8 cell codes (f32 at the API) / f64 geometry", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 cells / f64 geometry", "data": "synthetic",
         "config": workload_config(args.workload, world, (args.robots or arm.cfg["robots"]) * (world if args.scaling == "weak" else 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
