@@ -52,7 +52,14 @@ struct b200nav_ctx {
   std::vector<cudaEvent_t> copy_events;
   bool prep_done_valid = false;            /* copy_events[6] = "the last binning kernel has consumed the staged cloud" */
   cudaEvent_t fences[8] = {nullptr};       /* b200nav_ctx_fence / b200nav_ctx_wait */
+  cudaEvent_t fences_side[8] = {nullptr};  /* the same tickets on the side stream (asynchronous VFH+ updates) */
+  bool fence_has_side[8] = {false};
   int fence_seq = 0;
+  /* asynchronous batched VFH+ updates run on a side stream so that the NEXT cycle's copies, L2 traffic and binning
+   * kernel overlap them; `side_pending` = work on the side stream the main stream has not waited for yet */
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_to_side = nullptr, ev_side_done = nullptr;
+  bool side_pending = false;
   ProfSlot prof[PROF_KINDS];
   char err[512] = {0};
 };
@@ -171,8 +178,26 @@ struct b200nav_vfh {
 
 namespace {
 
+/* Host-side wait for the main stream and the side stream. */
+cudaError_t sync_raw(b200nav_ctx* ctx) {
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && ctx->side_stream) e = cudaStreamSynchronize(ctx->side_stream);
+  if (e == cudaSuccess) ctx->side_pending = false;
+  return e;
+}
+
+/* Make the main stream wait for whatever is in flight on the side stream (see b200nav_ctx::side_stream).  Called by
+ * everything that writes a layer, touches VFH+ state or frees buffers. */
+int join_side(b200nav_ctx* ctx) {
+  if (ctx->side_pending) {
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0));
+    ctx->side_pending = false;
+  }
+  return B200NAV_OK;
+}
+
 int sync_stream(b200nav_ctx* ctx) {
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, sync_raw(ctx));
   return B200NAV_OK;
 }
 
@@ -188,7 +213,8 @@ struct ProfScope {
   b200nav_ctx* ctx;
   int kind;
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-  ProfScope(b200nav_ctx* c, int k) : ctx(c), kind(k) {
+  cudaStream_t st;
+  ProfScope(b200nav_ctx* c, int k, cudaStream_t stream = nullptr) : ctx(c), kind(k), st(stream ? stream : c->stream) {
     if (!ctx->profiling) return;
     ProfSlot& s = ctx->prof[kind];
     if (!s.free_pairs.empty()) {
@@ -198,11 +224,11 @@ struct ProfScope {
       ev = {nullptr, nullptr};
       return;
     }
-    cudaEventRecord(ev.first, ctx->stream);
+    cudaEventRecord(ev.first, st);
   }
   ~ProfScope() {
     if (!ev.first) return;
-    cudaEventRecord(ev.second, ctx->stream);
+    cudaEventRecord(ev.second, st);
     ctx->prof[kind].pairs.push_back(ev);
   }
 };
@@ -293,7 +319,7 @@ int layer_to_float(b200nav_grid* g, Layer* l) {
   coded_to_float_kernel<<<conv_blocks(g, g->layer_elems(), 256), 256, 0, ctx->stream>>>(
       l->cdev(), f, g->dims.rows, g->dims.cols, grid_tiles_r(g), coded_robot_bytes(g), g->layer_elems());
   int rc = check_launch(ctx, "coded_to_float_kernel");
-  if (rc == B200NAV_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = B200NAV_ECUDA;
+  if (rc == B200NAV_OK && sync_raw(ctx) != cudaSuccess) rc = B200NAV_ECUDA;
   if (rc) {
     cudaFree(f);
     return rc;
@@ -332,7 +358,7 @@ int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words, si
   b200nav_ctx* ctx = g->ctx;
   const size_t mb = n_tiles_total * (size_t)mask_words * sizeof(uint32_t);
   if (mb > g->beam_masks.cap) {
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, sync_raw(ctx));
     CUDA_TRY(ctx, g->beam_masks.reserve(mb));
     CUDA_TRY(ctx, cudaMemsetAsync(g->beam_masks.p, 0, g->beam_masks.cap, ctx->stream));
   }
@@ -343,7 +369,7 @@ int himm_reserve_masks(b200nav_grid* g, size_t n_tiles_total, int mask_words, si
     CUDA_TRY(ctx, cudaMemsetAsync(g->counters.p, 0, g->counters.cap, ctx->stream));
   }
   if (n_robot_tiles * sizeof(uint32_t) > g->touched.cap) {
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, sync_raw(ctx));
     CUDA_TRY(ctx, g->touched.reserve(n_robot_tiles * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMemsetAsync(g->touched.p, 0, g->touched.cap, ctx->stream));
     CUDA_TRY(ctx, g->worklist.reserve(n_robot_tiles * sizeof(int)));
@@ -433,6 +459,8 @@ int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int 
 
 int himm_launch_tile(b200nav_grid* g, const HimmArgs& a) {
   b200nav_ctx* ctx = g->ctx;
+  int jrc = join_side(ctx); /* a VFH+ update on the side stream may still read the layer this kernel rewrites */
+  if (jrc) return jrc;
   /* persistent: as many one-warp CTAs as can be resident (32 per SM), never more than there are tiles */
   dim3 grid((unsigned)std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * 32));
   {
@@ -547,8 +575,9 @@ size_t vfh_smem_bytes(const b200nav_vfh* v, bool from_grid, int box_r, int box_c
 }
 
 int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const Layer* layer, const b200nav_vfh_input* dev_in,
-               const double* dev_ranges, b200nav_command* dev_out, int robot0, int n) {
+               const double* dev_ranges, b200nav_command* dev_out, int robot0, int n, cudaStream_t stream = nullptr) {
   b200nav_ctx* ctx = v->ctx;
+  if (!stream) stream = ctx->stream;
   VfhGridArgs ga;
   memset(&ga, 0, sizeof(ga));
   CUtensorMap tm;
@@ -571,13 +600,13 @@ int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const Layer* layer, const b200na
     smem = vfh_smem_bytes(v, true, box_r, box_c);
     if (smem > (size_t)kVfhMaxSmem) return set_err(ctx, B200NAV_ERANGE, "VFH window too large for shared memory (%zu B)", smem);
     auto kern = vfh_update_kernel<true>;
-    ProfScope ps(ctx, PROF_VFH);
-    kern<<<n, B200NAV_VFH_THREADS, smem, ctx->stream>>>(v->dev, ga, tm, dev_in, nullptr, dev_out, robot0);
+    ProfScope ps(ctx, PROF_VFH, stream);
+    kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, nullptr, dev_out, robot0);
   } else {
     smem = vfh_smem_bytes(v, false, 0, 0);
     auto kern = vfh_update_kernel<false>;
-    ProfScope ps(ctx, PROF_VFH);
-    kern<<<n, B200NAV_VFH_THREADS, smem, ctx->stream>>>(v->dev, ga, tm, dev_in, dev_ranges, dev_out, robot0);
+    ProfScope ps(ctx, PROF_VFH, stream);
+    kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, dev_ranges, dev_out, robot0);
   }
   return check_launch(ctx, "vfh_update_kernel");
 }
@@ -646,7 +675,8 @@ int b200nav_ctx_create(int device, void* cuda_stream, b200nav_ctx** out) {
 int b200nav_ctx_destroy(b200nav_ctx* ctx) {
   if (!ctx) return B200NAV_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  sync_raw(ctx);
+  if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
   prof_drain(ctx);
   for (int k = 0; k < PROF_KINDS; k++)
     for (auto& p : ctx->prof[k].free_pairs) {
@@ -656,6 +686,14 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
   for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->fences)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->fences_side)
+    if (e) cudaEventDestroy(e);
+  if (ctx->side_stream) {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+  }
+  if (ctx->ev_to_side) cudaEventDestroy(ctx->ev_to_side);
+  if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -673,9 +711,17 @@ int b200nav_ctx_synchronize(b200nav_ctx* ctx) {
 int b200nav_ctx_fence(b200nav_ctx* ctx, int* ticket) {
   if (!ctx || !ticket) return B200NAV_EINVAL;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  cudaEvent_t& e = ctx->fences[ctx->fence_seq & 7];
+  const int slot = ctx->fence_seq & 7;
+  cudaEvent_t& e = ctx->fences[slot];
   if (!e) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CUDA_TRY(ctx, cudaEventRecord(e, ctx->stream));
+  ctx->fence_has_side[slot] = false;
+  if (ctx->side_pending) { /* the ticket also covers the side stream, without serialising the two streams */
+    cudaEvent_t& es = ctx->fences_side[slot];
+    if (!es) CUDA_TRY(ctx, cudaEventCreateWithFlags(&es, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(es, ctx->side_stream));
+    ctx->fence_has_side[slot] = true;
+  }
   *ticket = ctx->fence_seq++;
   return B200NAV_OK;
 }
@@ -684,6 +730,7 @@ int b200nav_ctx_wait(b200nav_ctx* ctx, int ticket) {
   if (!ctx || ticket < 0 || ticket >= ctx->fence_seq) return B200NAV_EINVAL;
   /* a slot that was re-armed since marks a LATER point of the stream: waiting for it is still correct */
   CUDA_TRY(ctx, cudaEventSynchronize(ctx->fences[ticket & 7]));
+  if (ctx->fence_has_side[ticket & 7]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->fences_side[ticket & 7]));
   return B200NAV_OK;
 }
 
@@ -695,7 +742,8 @@ int64_t b200nav_ctx_launch_count(b200nav_ctx* ctx) { return ctx ? ctx->launches 
 
 int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable) {
   if (!ctx) return B200NAV_EINVAL;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int src = sync_stream(ctx);
+  if (src) return src;
   prof_drain(ctx);
   ctx->profiling = enable != 0;
   if (enable)
@@ -708,7 +756,8 @@ int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable) {
 
 int b200nav_ctx_profile_read(b200nav_ctx* ctx, const char* name, double* total_ms, int64_t* launches) {
   if (!ctx || !name) return B200NAV_EINVAL;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int src = sync_stream(ctx);
+  if (src) return src;
   prof_drain(ctx);
   for (int k = 0; k < PROF_KINDS; k++)
     if (strcmp(name, kProfNames[k]) == 0) {
@@ -760,7 +809,7 @@ int b200nav_grid_create(b200nav_ctx* ctx, double len_x, double len_y, double res
 int b200nav_grid_destroy(b200nav_grid* g) {
   if (!g) return B200NAV_OK;
   cudaSetDevice(g->ctx->device);
-  cudaStreamSynchronize(g->ctx->stream);
+  sync_raw(g->ctx);
   g->layers.clear(); /* frees the device buffers */
   g->stage.release();
   g->convflag.release();
@@ -817,7 +866,7 @@ int b200nav_grid_alias_layer(b200nav_grid* g, const char* alias, const char* tar
   Layer* t = find_layer(g, target);
   if (!t) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", target);
   if (find_layer(g, alias) == t) return B200NAV_OK;
-  cudaStreamSynchronize(g->ctx->stream); /* a layer replaced by the alias may still be in use */
+  sync_raw(g->ctx); /* a layer replaced by the alias may still be in use */
   g->layers[alias] = g->layers[target];
   return B200NAV_OK;
 }
@@ -827,8 +876,9 @@ int b200nav_grid_copy_layer(b200nav_grid* g, const char* dst, const char* src) {
   Layer *d = find_layer(g, dst), *s = find_layer(g, src);
   if (!d || !s) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", !d ? dst : src);
   if (d == s) return B200NAV_OK;
+  { int jrc = join_side(g->ctx); if (jrc) return jrc; }
   if (d->coded != s->coded) { /* the destination takes the source's format */
-    CUDA_TRY(g->ctx, cudaStreamSynchronize(g->ctx->stream));
+    CUDA_TRY(g->ctx, sync_raw(g->ctx));
     void* nd = nullptr;
     const size_t nbytes = s->coded ? coded_robot_bytes(g) * g->n_robots : g->layer_elems() * sizeof(float);
     CUDA_TRY(g->ctx, cudaMalloc(&nd, nbytes));
@@ -846,6 +896,7 @@ int b200nav_grid_copy_layer(b200nav_grid* g, const char* dst, const char* src) {
 
 int b200nav_grid_clear(b200nav_grid* g, const char* layer) {
   if (!g) return B200NAV_EINVAL;
+  { int jrc = join_side(g->ctx); if (jrc) return jrc; }
   if (layer) {
     Layer* l = find_layer(g, layer);
     if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer);
@@ -869,6 +920,7 @@ int b200nav_grid_upload(b200nav_grid* g, int robot, const char* layer, const flo
   const size_t n = (size_t)g->dims.rows * g->dims.cols;
   b200nav_ctx* ctx = g->ctx;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  { int jrc = join_side(ctx); if (jrc) return jrc; }
   int rrc = reset_free_cols(g, l, robot);
   if (rrc) return rrc;
   if (l->coded) {
@@ -887,7 +939,7 @@ int b200nav_grid_upload(b200nav_grid* g, int robot, const char* layer, const flo
       if (pass == 0) {
         int bad = 0;
         CUDA_TRY(ctx, cudaMemcpyAsync(&bad, g->convflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, sync_raw(ctx));
         if (bad) { /* values outside the HIMM set: the layer leaves the coded format */
           rc = layer_to_float(g, l);
           if (rc) return rc;
@@ -951,6 +1003,7 @@ int b200nav_grid_get_geometry(const b200nav_grid* g, int robot, double* pos_x, d
 
 int b200nav_grid_move(b200nav_grid* g, int robot, double x, double y, int* moved) {
   if (!g || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  { int jrc = join_side(g->ctx); if (jrc) return jrc; }
   /* GridMap::move (GridMap.cpp:346-412).  The index/position bookkeeping is a handful of scalar operations and
    * stays on the host (the GridMap object owns its geometry); the strips that fall out of the map are NaN-filled
    * on the device in every layer. */
@@ -1333,7 +1386,7 @@ static int himm_update_scans(b200nav_grid* g, const char* layer, const b200nav_s
     if ((long long)n_used * nr > 0x7fffffffLL) return set_err(ctx, B200NAV_ERANGE, "too many samples for one update");
     std::vector<int32_t> offs((size_t)nr + 1);
     for (int r = 0; r <= nr; r++) offs[r] = r * n_used;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); /* an earlier update may still read the cached arrays */
+    CUDA_TRY(ctx, sync_raw(ctx)); /* an earlier update may still read the cached arrays */
     CUDA_TRY(ctx, g->scan_sel.reserve(sizeof(int32_t) * (size_t)std::max(n_used, 1)));
     CUDA_TRY(ctx, g->scan_offsets.reserve(sizeof(int32_t) * ((size_t)nr + 1)));
     CUDA_TRY(ctx, cudaMemcpy(g->scan_sel.p, sel.data(), sizeof(int32_t) * (size_t)n_used, cudaMemcpyHostToDevice));
@@ -1495,7 +1548,7 @@ int b200nav_vfh_create(b200nav_ctx* ctx, const b200nav_vfh_params* p, int n_robo
 int b200nav_vfh_destroy(b200nav_vfh* v) {
   if (!v) return B200NAV_OK;
   cudaSetDevice(v->ctx->device);
-  cudaStreamSynchronize(v->ctx->stream);
+  sync_raw(v->ctx);
   cudaFree(v->d_dir);
   cudaFree(v->d_dist);
   cudaFree(v->d_base);
@@ -1522,7 +1575,7 @@ int b200nav_vfh_destroy(b200nav_vfh* v) {
 
 int b200nav_vfh_set_current_max_speed(b200nav_vfh* v, int max_speed) {
   if (!v || max_speed < 1) return B200NAV_EINVAL;
-  CUDA_TRY(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+  CUDA_TRY(v->ctx, sync_raw(v->ctx));
   vfh_build_min_turning_radius(v->tab, v->params, max_speed);
   int rc = upload_vec(v->ctx, &v->d_mtr, v->tab.min_turning_radius);
   if (rc) return rc;
@@ -1553,9 +1606,19 @@ static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int 
   CUDA_TRY(ctx, v->out_buf.reserve(sizeof(b200nav_command) * (size_t)n));
   const b200nav_vfh_input* dev_in = nullptr;
   int slot = -1;
+  cudaStream_t run = ctx->stream; /* stream of the kernel and of the command copy */
   if (!wait && ctx->copy_stream) {
-    /* pipelined cycles: the (small) input copy must not queue behind the next cycle's cloud on the copy engine, so
-     * it is issued on the copy stream as early as the slot's previous reader allows */
+    /* Pipelined cycles.  (1) The (small) input copy must not queue behind the next cycle's cloud on the copy engine:
+     * it is issued on the copy stream as early as the slot's previous reader allows.  (2) The kernel and the copy of
+     * the commands run on the side stream, after everything enqueued on the main stream so far (the tile kernel of
+     * this cycle): the next cycle's L2 traffic, copies and binning kernel overlap them, and the next tile kernel
+     * (the next writer of the layer) joins the side stream first (join_side). */
+    if (!ctx->side_stream) {
+      CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_to_side, cudaEventDisableTiming));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming));
+    }
+    run = ctx->side_stream;
     slot = v->in_slot;
     v->in_slot ^= 1;
     CUDA_TRY(ctx, v->in2[slot].reserve(sizeof(b200nav_vfh_input) * (size_t)n));
@@ -1565,9 +1628,13 @@ static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int 
     CUDA_TRY(ctx, cudaMemcpyAsync(v->in2[slot].p, host_in, sizeof(b200nav_vfh_input) * (size_t)n,
                                   cudaMemcpyHostToDevice, ctx->copy_stream));
     CUDA_TRY(ctx, cudaEventRecord(v->in_ready, ctx->copy_stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, v->in_ready, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_to_side, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev_to_side, 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(run, v->in_ready, 0));
     dev_in = static_cast<const b200nav_vfh_input*>(v->in2[slot].p);
   } else {
+    int jrc = join_side(ctx);
+    if (jrc) return jrc;
     CUDA_TRY(ctx, v->in_buf.reserve(sizeof(b200nav_vfh_input) * (size_t)n));
     CUDA_TRY(ctx, cudaMemcpyAsync(v->in_buf.p, host_in, sizeof(b200nav_vfh_input) * (size_t)n, cudaMemcpyHostToDevice,
                                   ctx->stream));
@@ -1580,14 +1647,17 @@ static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int 
                                   cudaMemcpyHostToDevice, ctx->stream));
     dr = static_cast<const double*>(v->ranges_buf.p);
   }
-  int rc = vfh_launch(v, g, lay, dev_in, dr, static_cast<b200nav_command*>(v->out_buf.p), robot0, n);
+  int rc = vfh_launch(v, g, lay, dev_in, dr, static_cast<b200nav_command*>(v->out_buf.p), robot0, n, run);
   if (rc) return rc;
   if (slot >= 0) {
-    CUDA_TRY(ctx, cudaEventRecord(v->in_done[slot], ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(v->in_done[slot], run));
     v->in_done_set[slot] = true;
   }
-  CUDA_TRY(ctx, cudaMemcpyAsync(host_out, v->out_buf.p, sizeof(b200nav_command) * (size_t)n, cudaMemcpyDeviceToHost,
-                                ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(host_out, v->out_buf.p, sizeof(b200nav_command) * (size_t)n, cudaMemcpyDeviceToHost, run));
+  if (run != ctx->stream) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_side_done, run));
+    ctx->side_pending = true;
+  }
   return wait ? sync_stream(ctx) : B200NAV_OK;
 }
 
@@ -1624,6 +1694,7 @@ int b200nav_vfh_update_batched_dev(b200nav_vfh* v, b200nav_grid* g, const char* 
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(v->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   CUDA_TRY(v->ctx, cudaSetDevice(v->ctx->device));
+  { int jrc = join_side(v->ctx); if (jrc) return jrc; }
   return vfh_launch(v, g, l, dev_in, nullptr, dev_out, 0, v->n_robots);
 }
 
@@ -1632,7 +1703,7 @@ int b200nav_vfh_read_state(b200nav_vfh* v, int robot, float* origin_hist, float*
   if (!v || robot < 0 || robot >= v->n_robots) return B200NAV_EINVAL;
   b200nav_ctx* ctx = v->ctx;
   const size_t H = v->tab.c.hist_size;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, sync_raw(ctx));
   if (origin_hist)
     CUDA_TRY(ctx, cudaMemcpy(origin_hist, v->dev.origin_hist + H * robot, sizeof(float) * H, cudaMemcpyDeviceToHost));
   if (hist) CUDA_TRY(ctx, cudaMemcpy(hist, v->dev.hist + H * robot, sizeof(float) * H, cudaMemcpyDeviceToHost));
@@ -1658,7 +1729,7 @@ int b200nav_vfh_read_state(b200nav_vfh* v, int robot, float* origin_hist, float*
 int b200nav_vfh_read_ranges(b200nav_vfh* v, int robot, double* ranges361x2) {
   if (!v || !ranges361x2 || robot < 0 || robot >= v->n_robots) return B200NAV_EINVAL;
   double tmp[B200NAV_NRANGES];
-  CUDA_TRY(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+  CUDA_TRY(v->ctx, sync_raw(v->ctx));
   CUDA_TRY(v->ctx, cudaMemcpy(tmp, v->dev.ranges + (size_t)B200NAV_NRANGES * robot, sizeof(tmp), cudaMemcpyDeviceToHost));
   for (int i = 0; i < B200NAV_NRANGES; i++) {
     ranges361x2[2 * i] = tmp[i];
@@ -1689,7 +1760,7 @@ int b200nav_himm_debug_tile_stats(b200nav_grid* g, int64_t* out2) {
   out2[0] = out2[1] = 0;
   if (!g->counters.p) return B200NAV_OK;
   int c[8];
-  CUDA_TRY(g->ctx, cudaStreamSynchronize(g->ctx->stream));
+  CUDA_TRY(g->ctx, sync_raw(g->ctx));
   CUDA_TRY(g->ctx, cudaMemcpy(c, g->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
   out2[0] = c[4];
   out2[1] = c[5];

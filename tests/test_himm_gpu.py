@@ -331,11 +331,19 @@ def test_async_cycles_overlap_and_match_synchronous_calls(ctx):
         grids[0].himm_update_cloud_batched_async("laser", d["origins"], d["xy"], d["clear"], d["offsets"])
         vfhs[0].update_batched_async(grids[0], "laser", d["inp"], d["out"])
         tickets.append(ctx.fence())
+        if c == 2:   # stream-ordered writers / state readers in the middle of the pipeline (they join the side stream)
+            grids[0].move((0.5, -0.25), robot=2)
+            mid_state = vfhs[0].state(robot=3)
     want = []
-    for d in data:
+    for c, d in enumerate(data):
         grids[1].himm_update_cloud_batched("laser", d["origins"].numpy(), d["xy"].numpy(), d["clear"].numpy(),
                                            d["offsets"].numpy())
         want.append(vfhs[1].update_batched(grids[1], "laser", d["inp_np"]))
+        if c == 2:
+            grids[1].move((0.5, -0.25), robot=2)
+            ref_state = vfhs[1].state(robot=3)
+            for k in ref_state:
+                assert np.array_equal(np.asarray(mid_state[k]), np.asarray(ref_state[k])), k
     for c in (3, 0, 5):
         ctx.wait(tickets[c])
         got = data[c]["out"].numpy().view(capi.COMMAND_DTYPE).reshape(-1)
