@@ -260,11 +260,10 @@ class GpuArm:
         self.vfh = VFH(self.ctx, VfhParams(window_diameter=cfg["window"], cell_size=cfg["cell"],
                                            submap_length=cfg["submap"]), n_robots=self.n)
         from ros_navigation_b200.dist import CommandExchange
-        self.exchange = CommandExchange(robots_total, device) if world > 1 else None
+        self.exchange = (CommandExchange(robots_total, device, ctx=None if os.environ.get("B200NAV_TORCH_EXCHANGE") else self.ctx)
+                         if (world > 1 and not os.environ.get("B200NAV_BENCH_NO_EXCHANGE")) else None)
         self.cmd = self.exchange.local if self.exchange else torch.zeros(self.n, 16, dtype=torch.uint8, device=device)
         self.gathered = self.exchange.table if self.exchange else None
-        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
-        self.flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=device)
         # pinned host copies for the end-to-end path
         self.h_origins = [o.cpu().pin_memory() for o in self.cyc.origins]
         self.h_xy = [o.cpu().pin_memory() for o in self.cyc.xy]
@@ -358,19 +357,19 @@ class GpuArm:
 def flush_l2_light(arm):
     """In-stream flush for the pipelined end-to-end loop: write a buffer larger than L2 (160 MiB > 126 MB).  The
     write-back of these lines happens inside the timed region like everything else there."""
-    arm.flush[:L2_FLUSH_LIGHT_BYTES].zero_()
+    arm.ctx.flush_l2(L2_FLUSH_LIGHT_BYTES, 0)
 
 
 def flush_l2(arm):
     """Write a 256 MiB buffer (evicts everything), then read another 256 MiB one so that the dirty lines of the
     write are themselves written back BEFORE the timed step starts (their write-back is not our kernels' traffic)."""
-    arm.flush.zero_()
-    arm.flush_rd.max()
+    arm.ctx.flush_l2(L2_FLUSH_BYTES, L2_FLUSH_BYTES)
 
 
 def timed_steps(torch, stream, step_fn, first, n, arm):
     """n steps, each bracketed by CUDA events on `stream`, L2 flushed before every step. Returns ms list."""
     evs = []
+    t0 = time.perf_counter()
     for k in range(n):
         flush_l2(arm)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -378,6 +377,7 @@ def timed_steps(torch, stream, step_fn, first, n, arm):
         step_fn(first + k, last=(k == n - 1))
         b.record(stream)
         evs.append((a, b))
+    arm.host_enqueue_ms_per_step = (time.perf_counter() - t0) * 1000.0 / max(n, 1)   # host side of the loop alone
     stream.synchronize()
     return [a.elapsed_time(b) for a, b in evs]
 
@@ -490,6 +490,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "kernel_ms_per_step": {"himm_prep": prep_ms / max(prep_n, 1), "himm_tile": tile_avg_ms,
                                "vfh_update": vfh_ms / max(vfh_n, 1)},
         "wall_s_timed_region": wall,
+        "host_enqueue_ms_per_step": getattr(arm, "host_enqueue_ms_per_step", None),
     }
     # the two smaller kernels against the same HBM peak (SURVEY section 8d accounting; both are latency bound)
     beams = float(np.mean([u[3] for u in used]))

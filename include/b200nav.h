@@ -57,6 +57,9 @@ int b200nav_ctx_synchronize(b200nav_ctx* ctx);
 /* Pipelining aid for the *_async entry points: fence() marks the current end of the context's stream and returns a
  * ticket; wait() blocks the calling thread until everything enqueued before that fence has completed (tickets may be
  * waited for in any order; only the 8 most recent fences are distinguishable, older ones wait a little longer). */
+/* Measurement aid for bench.py: streams write_bytes (stores) and then read_bytes (loads) of scratch memory through
+ * L2 on the context's stream so that a following step starts with a cold cache. */
+int b200nav_ctx_flush_l2(b200nav_ctx* ctx, size_t write_bytes, size_t read_bytes);
 int b200nav_ctx_fence(b200nav_ctx* ctx, int* ticket);
 int b200nav_ctx_wait(b200nav_ctx* ctx, int ticket);
 void* b200nav_ctx_stream(b200nav_ctx* ctx);
@@ -128,6 +131,24 @@ int b200nav_grid_has_layer(const b200nav_grid* grid, const char* layer);
 #define B200NAV_LAYER_FLOAT 0
 #define B200NAV_LAYER_CODED 1
 int b200nav_grid_layer_format(b200nav_grid* grid, const char* layer);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Fleet: batched multi-GPU mode (no counterpart in the reference: one robot, one process).  One process per GPU,
+ * robots block-partitioned, NO collective on grids or scans; once per cycle the 16-byte b200nav_command records of
+ * all robots are all-gathered over NVLink so that every rank sees the whole fleet.  NCCL is bound at run time
+ * (libnccl.so.2 via dlopen).  The gather runs on its own stream: start it after the VFH+ update that wrote
+ * dev_local, keep launching the next cycle, and call b200nav_fleet_wait(slot) before anything on the context's
+ * stream reads dev_table or rewrites dev_local (two slots = double buffering).
+ *   id128: 128 bytes from b200nav_fleet_unique_id on rank 0, distributed to all ranks by the launcher.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct b200nav_fleet b200nav_fleet;
+int b200nav_fleet_unique_id(uint8_t* id128);
+int b200nav_fleet_create(b200nav_ctx* ctx, const uint8_t* id128, int rank, int world, b200nav_fleet** out);
+int b200nav_fleet_gather_async(b200nav_fleet* fleet, int slot, const void* dev_local, void* dev_table,
+                               size_t bytes_per_rank);
+/* slot < 0: both slots. */
+int b200nav_fleet_wait(b200nav_fleet* fleet, int slot);
+int b200nav_fleet_destroy(b200nav_fleet* fleet);
 
 /* ------------------------------------------------------------------------------------------------------
  * HIMM update.  Replaces LaserMapUpdater::updateMap / RangeMapUpdater::updateMap

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "b200nav_grid_query_blocked": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "b200nav_grid_layer_written": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "b200nav_grid_layer_devptr": (C.c_void_p, [C.c_void_p, C.c_char_p]),
+    "b200nav_ctx_flush_l2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "b200nav_ctx_fence": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "b200nav_ctx_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_himm_update_cloud_batched_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -78,6 +79,11 @@ _SIGNATURES = {
     "b200nav_scan_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "b200nav_himm_update_scans_batched": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200nav_himm_update_scans_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200nav_fleet_unique_id": (C.c_int, [C.c_void_p]),
+    "b200nav_fleet_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200nav_fleet_gather_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200nav_fleet_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200nav_fleet_destroy": (C.c_int, [C.c_void_p]),
     "b200nav_grid_has_layer": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_grid_layer_format": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_update": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -164,6 +170,9 @@ class Context:
 
     def synchronize(self):
         check(lib().b200nav_ctx_synchronize(self.h), self.h)
+
+    def flush_l2(self, write_bytes, read_bytes=0):
+        check(lib().b200nav_ctx_flush_l2(self.h, int(write_bytes), int(read_bytes)), self.h)
 
     def fence(self):
         """Mark the current end of the stream; returns a ticket for wait()."""

@@ -5,6 +5,7 @@
  * sm_100a kernels of himm_kernels.cuh / vfh_kernels.cuh / grid_kernels.cuh; there is no CPU fallback.
  */
 #include <cuda.h>
+#include <dlfcn.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -57,6 +58,8 @@ struct b200nav_ctx {
   int fence_seq = 0;
   /* asynchronous batched VFH+ updates run on a side stream so that the NEXT cycle's copies, L2 traffic and binning
    * kernel overlap them; `side_pending` = work on the side stream the main stream has not waited for yet */
+  void* flush_buf = nullptr;               /* b200nav_ctx_flush_l2 scratch: [write half | read half] */
+  size_t flush_cap = 0;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_to_side = nullptr, ev_side_done = nullptr;
   bool side_pending = false;
@@ -148,6 +151,24 @@ struct b200nav_grid {
   DevBuf stage, convflag; /* float staging for upload / download of CODED layers; conversion "bad value" flag */
   int last_total = 0;
   size_t layer_elems() const { return (size_t)n_robots * dims.rows * dims.cols; }
+};
+
+/* Batched multi-GPU mode: the once-per-cycle all-gather of the robots' 16-byte commands (one process per GPU, robots
+ * block-partitioned; no collective touches grids or scans).  NCCL is bound at run time (dlopen) so that the library
+ * has no link-time dependency on it; the collective runs on its own stream and overlaps the next cycle's kernels. */
+struct b200nav_fleet {
+  b200nav_ctx* ctx = nullptr;
+  void* lib = nullptr;
+  struct NcclId { char internal[128]; };
+  int (*InitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*ErrorString)(int) = nullptr;
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+  bool pending[2] = {false, false};
 };
 
 struct b200nav_vfh {
@@ -692,6 +713,7 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
   }
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->ev_to_side) cudaEventDestroy(ctx->ev_to_side);
   if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
   if (ctx->copy_stream) {
@@ -706,6 +728,29 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
 int b200nav_ctx_synchronize(b200nav_ctx* ctx) {
   if (!ctx) return B200NAV_EINVAL;
   return sync_stream(ctx);
+}
+
+int b200nav_ctx_flush_l2(b200nav_ctx* ctx, size_t write_bytes, size_t read_bytes) {
+  if (!ctx) return B200NAV_EINVAL;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t w16 = write_bytes / 16, r16 = read_bytes / 16;
+  if ((w16 + r16) * 16 > ctx->flush_cap) {
+    CUDA_TRY(ctx, sync_raw(ctx));
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    ctx->flush_buf = nullptr;
+    ctx->flush_cap = 0;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->flush_buf, (w16 + r16) * 16 + 16));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->flush_buf, 0, (w16 + r16) * 16 + 16, ctx->stream));
+    ctx->flush_cap = (w16 + r16) * 16;
+  }
+  uint4* base = static_cast<uint4*>(ctx->flush_buf);
+  unsigned* sink = reinterpret_cast<unsigned*>(base + w16 + r16);
+  const unsigned blocks = (unsigned)ctx->sm_count * 8;
+  if (w16) l2_flush_kernel<<<blocks, 256, 0, ctx->stream>>>(base, w16, 1, sink);
+  if (r16) l2_flush_kernel<<<blocks, 256, 0, ctx->stream>>>(base + w16, r16, 2, sink);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(ctx, B200NAV_ECUDA, "l2_flush_kernel: %s", cudaGetErrorString(e));
+  return B200NAV_OK; /* not counted in launch_count: a measurement aid, not part of the path */
 }
 
 int b200nav_ctx_fence(b200nav_ctx* ctx, int* ticket) {
@@ -746,6 +791,13 @@ int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable) {
   if (src) return src;
   prof_drain(ctx);
   ctx->profiling = enable != 0;
+  if (enable) /* event pairs are only recycled at drain points: have enough ready so that timed launches create none */
+    for (int k = 0; k < PROF_KINDS; k++)
+      while (ctx->prof[k].free_pairs.size() < 512) {
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) break;
+        ctx->prof[k].free_pairs.push_back(ev);
+      }
   if (enable)
     for (int k = 0; k < PROF_KINDS; k++) {
       ctx->prof[k].total_ms = 0;
@@ -1135,6 +1187,93 @@ int b200nav_grid_layer_format(b200nav_grid* g, const char* layer) {
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
   return l->coded ? B200NAV_LAYER_CODED : B200NAV_LAYER_FLOAT;
+}
+
+/* ================================================================================================================
+ * Fleet (multi-GPU command exchange)
+ * ============================================================================================================== */
+
+static void* nccl_open() {
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  return h;
+}
+
+int b200nav_fleet_unique_id(uint8_t* id128) {
+  if (!id128) return B200NAV_EINVAL;
+  void* h = nccl_open();
+  if (!h) return set_err(nullptr, B200NAV_ENODEVICE, "libnccl.so.2 not found: %s", dlerror());
+  auto get = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+  if (!get) return set_err(nullptr, B200NAV_ENODEVICE, "ncclGetUniqueId missing");
+  const int r = get(id128);
+  return r == 0 ? B200NAV_OK : set_err(nullptr, B200NAV_ECUDA, "ncclGetUniqueId failed (%d)", r);
+}
+
+int b200nav_fleet_create(b200nav_ctx* ctx, const uint8_t* id128, int rank, int world, b200nav_fleet** out) {
+  if (!ctx || !id128 || !out || world < 1 || rank < 0 || rank >= world) return B200NAV_EINVAL;
+  *out = nullptr;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<b200nav_fleet> f(new b200nav_fleet());
+  f->ctx = ctx;
+  f->rank = rank;
+  f->world = world;
+  f->lib = nccl_open();
+  if (!f->lib) return set_err(ctx, B200NAV_ENODEVICE, "libnccl.so.2 not found: %s", dlerror());
+  f->InitRank = reinterpret_cast<decltype(f->InitRank)>(dlsym(f->lib, "ncclCommInitRank"));
+  f->AllGather = reinterpret_cast<decltype(f->AllGather)>(dlsym(f->lib, "ncclAllGather"));
+  f->CommDestroy = reinterpret_cast<decltype(f->CommDestroy)>(dlsym(f->lib, "ncclCommDestroy"));
+  f->ErrorString = reinterpret_cast<decltype(f->ErrorString)>(dlsym(f->lib, "ncclGetErrorString"));
+  if (!f->InitRank || !f->AllGather || !f->CommDestroy) return set_err(ctx, B200NAV_ENODEVICE, "NCCL symbols missing");
+  b200nav_fleet::NcclId id;
+  memcpy(id.internal, id128, sizeof(id.internal));
+  const int r = f->InitRank(&f->comm, world, id, rank);
+  if (r != 0) return set_err(ctx, B200NAV_ECUDA, "ncclCommInitRank: %s", f->ErrorString ? f->ErrorString(r) : "?");
+  CUDA_TRY(ctx, cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->ready[i], cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&f->done[i], cudaEventDisableTiming));
+  }
+  *out = f.release();
+  return B200NAV_OK;
+}
+
+int b200nav_fleet_gather_async(b200nav_fleet* f, int slot, const void* dev_local, void* dev_table,
+                               size_t bytes_per_rank) {
+  if (!f || slot < 0 || slot > 1 || !dev_local || !dev_table) return B200NAV_EINVAL;
+  b200nav_ctx* ctx = f->ctx;
+  { int jrc = join_side(ctx); if (jrc) return jrc; }
+  /* after everything enqueued on the context's stream so far (the VFH+ kernel that wrote dev_local) */
+  CUDA_TRY(ctx, cudaEventRecord(f->ready[slot], ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(f->stream, f->ready[slot], 0));
+  const int r = f->AllGather(dev_local, dev_table, bytes_per_rank, /*ncclUint8*/ 1, f->comm, f->stream);
+  if (r != 0) return set_err(ctx, B200NAV_ECUDA, "ncclAllGather: %s", f->ErrorString ? f->ErrorString(r) : "?");
+  CUDA_TRY(ctx, cudaEventRecord(f->done[slot], f->stream));
+  f->pending[slot] = true;
+  return B200NAV_OK;
+}
+
+int b200nav_fleet_wait(b200nav_fleet* f, int slot) {
+  if (!f || slot > 1) return B200NAV_EINVAL;
+  for (int s = (slot < 0 ? 0 : slot); s <= (slot < 0 ? 1 : slot); s++)
+    if (f->pending[s]) { /* stream-side wait: later work on the context's stream sees the gathered table */
+      CUDA_TRY(f->ctx, cudaStreamWaitEvent(f->ctx->stream, f->done[s], 0));
+      f->pending[s] = false;
+    }
+  return B200NAV_OK;
+}
+
+int b200nav_fleet_destroy(b200nav_fleet* f) {
+  if (!f) return B200NAV_OK;
+  cudaSetDevice(f->ctx->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  if (f->comm && f->CommDestroy) f->CommDestroy(f->comm);
+  for (int i = 0; i < 2; i++) {
+    if (f->ready[i]) cudaEventDestroy(f->ready[i]);
+    if (f->done[i]) cudaEventDestroy(f->done[i]);
+  }
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+  return B200NAV_OK;
 }
 
 /* ================================================================================================================

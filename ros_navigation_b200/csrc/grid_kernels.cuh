@@ -96,5 +96,21 @@ __global__ void grid_blocked_kernel(GridDims d, RobotGeom g, const LayerRef laye
   if (lane == 0) out[q] = any ? 1 : 0;
 }
 
+/* Measurement aid (bench.py): stream `n16` 16-byte words through L2 - write them (mode 1), or read them and fold
+ * the result into *sink (mode 2) - so that nothing of the previous step is left in the cache. */
+__global__ void l2_flush_kernel(uint4* __restrict__ buf, size_t n16, int mode, unsigned* __restrict__ sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  unsigned acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    if (mode == 1) {
+      buf[i] = make_uint4((unsigned)i, 0u, 0u, 0u);
+    } else {
+      const uint4 v = buf[i];
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  }
+  if (mode == 2 && acc == 0x9e3779b9u) *sink = acc; /* keeps the loads alive */
+}
+
 }  // namespace b200nav
 #endif

@@ -28,9 +28,14 @@ def owner_of(robot, total, world):
 class CommandExchange:
     """Per-cycle all-gather of the local robots' command records into a [total, 16] uint8 table."""
 
-    def __init__(self, total, device, group=None):
+    def __init__(self, total, device, group=None, ctx=None):
+        """ctx: a capi.Context.  When given (CUDA, world > 1, equal shares) the gathers go through the library's own
+        NCCL binding (b200nav_fleet_*): a handful of driver calls per cycle instead of a torch.distributed collective,
+        which matters when the host, not the GPU, is the bottleneck of a sub-millisecond cycle."""
         self.total = total
         self.group = group
+        self.fleet = None
+        self.ctx = ctx
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.lo, self.hi = partition(total, self.rank, self.world)
@@ -42,9 +47,32 @@ class CommandExchange:
         self.tables = [torch.zeros(total, COMMAND_BYTES, dtype=torch.uint8, device=device) for _ in range(2)]
         self.local, self.table = self.locals[0], self.tables[0]
         self._pending = [None, None]
+        if ctx is not None and self.world > 1 and self.even and torch.device(device).type == "cuda":
+            self._init_fleet(device)
         if not self.even:  # padded staging so that every rank contributes the same number of bytes
             self._send = torch.zeros(self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
             self._recv = torch.zeros(self.world * self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
+
+    def _init_fleet(self, device):
+        import ctypes as C
+        from .capi import check, lib
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            check(lib().b200nav_fleet_unique_id(buf), None)
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(device)
+        dist.broadcast(ident, src=0, group=self.group)
+        raw = bytes(ident.cpu().tolist())
+        h = C.c_void_p()
+        check(lib().b200nav_fleet_create(self.ctx.h, raw, self.rank, self.world, C.byref(h)), self.ctx.h)
+        self.fleet = h
+
+    def close(self):
+        if self.fleet is not None:
+            from .capi import lib
+            lib().b200nav_fleet_destroy(self.fleet)
+            self.fleet = None
 
     def gather_async(self, slot):
         """Start the all-gather of `self.locals[slot]` into `self.tables[slot]` without blocking the caller's stream:
@@ -55,19 +83,34 @@ class CommandExchange:
             self.tables[slot].copy_(self.locals[slot])
             return
         assert self.even, "gather_async needs total % world == 0"
+        if self.fleet is not None:
+            from .capi import check, lib
+            check(lib().b200nav_fleet_gather_async(self.fleet, slot, self.locals[slot].data_ptr(),
+                                                   self.tables[slot].data_ptr(), self.n_local * COMMAND_BYTES),
+                  self.ctx.h)
+            self._pending[slot] = True
+            return
         self._pending[slot] = dist.all_gather_into_tensor(self.tables[slot].view(-1), self.locals[slot].view(-1),
                                                           group=self.group, async_op=True)
 
     def wait(self, slot=None):
         for s in ([slot] if slot is not None else [0, 1]):
             if self._pending[s] is not None:
-                self._pending[s].wait()
+                if self.fleet is not None:
+                    from .capi import check, lib
+                    check(lib().b200nav_fleet_wait(self.fleet, s), self.ctx.h)
+                else:
+                    self._pending[s].wait()
                 self._pending[s] = None
 
     def gather(self):
         """All ranks call this once per cycle after their VFH+ kernel wrote `self.local`. Returns `self.table`."""
         if self.world == 1:
             self.table.copy_(self.local)
+            return self.table
+        if self.fleet is not None:
+            self.gather_async(0)
+            self.wait(0)
             return self.table
         if self.even:
             dist.all_gather_into_tensor(self.table.view(-1), self.local.view(-1), group=self.group)
