@@ -61,6 +61,7 @@ class Cycles:
         self.dt = dt
         self.samples, self.offsets, self.inputs, self.totals = [], [], [], []
         self.origins, self.xy, self.clear = [], [], []
+        self.poses, self.ranges32 = [], []   # scan form (end-to-end path): sensor pose + raw float32 ranges
         for c in range(n_cycles):
             t = c * dt * 5  # spread the replayed poses a little so cycles are distinct
             x, y, yaw = self.worlds.pose(t)
@@ -70,6 +71,8 @@ class Cycles:
                 self.samples.append(s8.contiguous())
             else:             # compact cloud form (GPU arm): origin per robot + float32 end points
                 org, xy, clr, off = synth.cloud_from_scan(x, y, yaw, r, ang, cfg["range_max"])
+                self.poses.append(torch.stack([x, y, yaw], dim=1).contiguous())
+                self.ranges32.append(r.float().contiguous())
                 self.origins.append(org)
                 self.xy.append(xy)
                 self.clear.append(clr)
@@ -270,6 +273,10 @@ class GpuArm:
         self.h_clear = [o.cpu().pin_memory() for o in self.cyc.clear]
         self.h_offsets = [o.cpu().pin_memory() for o in self.cyc.offsets]
         self.h_inputs = [i.cpu().pin_memory() for i in self.cyc.inputs]
+        self.h_poses = [o.cpu().pin_memory() for o in self.cyc.poses]
+        self.h_ranges = [o.cpu().pin_memory() for o in self.cyc.ranges32]
+        self.scan_info = self.grid.scan_info(-cfg["fov"] / 2, cfg["fov"] / cfg["beams"], 0.0, cfg["range_max"],
+                                             cfg["beams"], decimate=False)
         self.d_inputs_e2e = torch.zeros_like(self.cyc.inputs[0])
         self.h_cmd = torch.zeros((robots_total if world > 1 else self.n), 16, dtype=torch.uint8).pin_memory()
         self.h_cmds = [self.h_cmd, torch.zeros_like(self.h_cmd).pin_memory()]
@@ -314,9 +321,10 @@ class GpuArm:
         self.h_cmd.copy_(src, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
 
-    def run_e2e_pipelined(self, first, n, flush=True, depth=2):
+    def run_e2e_pipelined(self, first, n, flush=True, depth=2, scans=True):
         """n end-to-end cycles through the asynchronous C-ABI calls, at most `depth` cycles in flight: every cycle
-        copies its cloud, offsets, origins and VFH inputs from pinned host memory, runs the three kernels and copies
+        copies its raw scans (float32 ranges + sensor poses; scans=False: the projected cloud) and VFH inputs from
+        pinned host memory, runs the three kernels and copies
         the commands (N > 1: the all-gathered table) back to pinned host memory.  The cloud copy of cycle i+1 overlaps
         the tile / VFH+ kernels of cycle i.  The L2 flush runs in-stream between cycles (inside the caller's timed
         region)."""
@@ -326,8 +334,11 @@ class GpuArm:
             c, slot = i % N_CYCLES, k & 1
             if flush:
                 flush_l2_light(self)
-            self.grid.himm_update_cloud_batched_async("laser", self.h_origins[c], self.h_xy[c], self.h_clear[c],
-                                                      self.h_offsets[c])
+            if scans:
+                self.grid.himm_update_scans_batched_async("laser", self.scan_info, self.h_poses[c], self.h_ranges[c])
+            else:
+                self.grid.himm_update_cloud_batched_async("laser", self.h_origins[c], self.h_xy[c], self.h_clear[c],
+                                                          self.h_offsets[c])
             if self.exchange is None:
                 self.vfh.update_batched_async(self.grid, "master", self.h_inputs[c], self.h_cmds[slot])
             else:
@@ -343,8 +354,7 @@ class GpuArm:
         self.ctx.synchronize()
 
     def e2e_bytes(self, c):
-        h2d = (self.h_origins[c].numel() * 8 + self.h_xy[c].numel() * 4 + self.h_clear[c].numel() +
-               self.h_offsets[c].numel() * 4 + self.h_inputs[c].numel())
+        h2d = self.h_poses[c].numel() * 8 + self.h_ranges[c].numel() * 4 + self.h_inputs[c].numel()
         return h2d, self.h_cmd.numel()
 
     def algorithmic_bytes(self, c):
@@ -477,7 +487,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / args.steps,
                 "how": "wall clock over all timed cycles through the asynchronous C-ABI calls, 2 cycles in flight: pinned "
-                       "host buffers in, commands back to pinned host memory; L2 is flushed in-stream before every "
+                       "host buffers in (raw float32 scans + sensor poses, projected on the device; VFH inputs), commands back to pinned host memory; L2 is flushed in-stream before every "
                        "cycle (160 MiB write) and that flush is INSIDE this time",
                 "l2_flush_ms_per_step": flush_s * 1000.0 / args.steps},
         "gpu_launches": int(launches),

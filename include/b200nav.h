@@ -217,6 +217,10 @@ typedef struct b200nav_scan_info {
 int b200nav_scan_select(const b200nav_scan_info* info, int32_t* sel, int cap, float* increment_used);
 int b200nav_himm_update_scans_batched(b200nav_grid* grid, const char* layer, const b200nav_scan_info* info,
                                       const double* host_poses, const float* host_ranges);
+/* Enqueue-only form (pinned host arrays, valid until the work completed: see b200nav_himm_update_cloud_batched_async);
+ * the copy of the next cycle's ranges overlaps the current cycle's tile and VFH+ kernels. */
+int b200nav_himm_update_scans_batched_async(b200nav_grid* grid, const char* layer, const b200nav_scan_info* info,
+                                            const double* host_poses, const float* host_ranges);
 /* Same with device arrays; asynchronous. */
 int b200nav_himm_update_scans_batched_dev(b200nav_grid* grid, const char* layer, const b200nav_scan_info* info,
                                           const double* dev_poses, const float* dev_ranges);

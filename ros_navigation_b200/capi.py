@@ -78,6 +78,7 @@ _SIGNATURES = {
     "b200nav_vfh_update_batched_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
     "b200nav_scan_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "b200nav_himm_update_scans_batched": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200nav_himm_update_scans_batched_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200nav_himm_update_scans_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200nav_fleet_unique_id": (C.c_int, [C.c_void_p]),
     "b200nav_fleet_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

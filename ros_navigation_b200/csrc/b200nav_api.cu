@@ -1509,8 +1509,11 @@ int b200nav_scan_select(const b200nav_scan_info* info, int32_t* sel, int cap, fl
   return n;
 }
 
+enum { SCANS_DEV = 0, SCANS_HOST = 1, SCANS_HOST_ASYNC = 2 };
+
 static int himm_update_scans(b200nav_grid* g, const char* layer, const b200nav_scan_info* info, const double* poses,
-                             const float* ranges, bool host) {
+                             const float* ranges, int mode) {
+  const bool host = mode != SCANS_DEV;
   if (!g || !info || !poses || !ranges || info->n_ranges <= 0) return B200NAV_EINVAL;
   Layer* l = find_layer(g, layer);
   if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
@@ -1538,12 +1541,31 @@ static int himm_update_scans(b200nav_grid* g, const char* layer, const b200nav_s
   const int n_used = g->scan_n_used;
   if (n_used == 0) return B200NAV_OK;
   CloudIn c;
+  const bool piped = mode == SCANS_HOST_ASYNC;
   if (host) {
     CUDA_TRY(ctx, g->scan_poses.reserve(sizeof(double) * 3 * (size_t)nr));
     CUDA_TRY(ctx, g->scan_ranges.reserve(sizeof(float) * (size_t)nr * info->n_ranges));
-    CUDA_TRY(ctx, cudaMemcpyAsync(g->scan_poses.p, poses, sizeof(double) * 3 * (size_t)nr, cudaMemcpyHostToDevice, ctx->stream));
+    cudaStream_t cs = ctx->stream;
+    if (piped) {
+      /* as in the asynchronous cloud update: the copies go on the copy stream and only wait for the last binning
+       * kernel that read the staging buffers, so they overlap the previous cycle's tile / VFH+ kernels */
+      if (!ctx->copy_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        ctx->copy_events.resize(8);
+        for (auto& e : ctx->copy_events) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
+      cs = ctx->copy_stream;
+      if (!ctx->prep_done_valid) CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[6], ctx->stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->copy_events[6], 0));
+    }
+    ctx->prep_done_valid = false;
+    CUDA_TRY(ctx, cudaMemcpyAsync(g->scan_poses.p, poses, sizeof(double) * 3 * (size_t)nr, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(g->scan_ranges.p, ranges, sizeof(float) * (size_t)nr * info->n_ranges,
-                                  cudaMemcpyHostToDevice, ctx->stream));
+                                  cudaMemcpyHostToDevice, cs));
+    if (piped) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[0], cs));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[0], 0));
+    }
     c.scan_poses = static_cast<const double*>(g->scan_poses.p);
     c.scan_ranges = static_cast<const float*>(g->scan_ranges.p);
   } else {
@@ -1557,19 +1579,33 @@ static int himm_update_scans(b200nav_grid* g, const char* layer, const b200nav_s
   c.scan.range_max = info->range_max;
   c.scan.n_ranges = info->n_ranges;
   c.scan.n_used = n_used;
-  int rc = himm_launch(g, l, nullptr, static_cast<const int32_t*>(g->scan_offsets.p), 0, nr, -1, nr * n_used, n_used, c);
+  HimmArgs a;
+  int rc = himm_setup(g, l, nullptr, static_cast<const int32_t*>(g->scan_offsets.p), 0, nr, -1, nr * n_used, n_used, c, a);
   if (rc) return rc;
-  return host ? sync_stream(ctx) : B200NAV_OK;
+  rc = himm_launch_prep(g, a, 0, nr * n_used, 0, nr);
+  if (rc) return rc;
+  if (piped) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->copy_events[6], ctx->stream));
+    ctx->prep_done_valid = true;
+  }
+  rc = himm_launch_tile(g, a);
+  if (rc) return rc;
+  return mode == SCANS_HOST ? sync_stream(ctx) : B200NAV_OK;
 }
 
 int b200nav_himm_update_scans_batched(b200nav_grid* g, const char* layer, const b200nav_scan_info* info,
                                       const double* host_poses, const float* host_ranges) {
-  return himm_update_scans(g, layer, info, host_poses, host_ranges, true);
+  return himm_update_scans(g, layer, info, host_poses, host_ranges, SCANS_HOST);
+}
+
+int b200nav_himm_update_scans_batched_async(b200nav_grid* g, const char* layer, const b200nav_scan_info* info,
+                                            const double* host_poses, const float* host_ranges) {
+  return himm_update_scans(g, layer, info, host_poses, host_ranges, SCANS_HOST_ASYNC);
 }
 
 int b200nav_himm_update_scans_batched_dev(b200nav_grid* g, const char* layer, const b200nav_scan_info* info,
                                           const double* dev_poses, const float* dev_ranges) {
-  return himm_update_scans(g, layer, info, dev_poses, dev_ranges, false);
+  return himm_update_scans(g, layer, info, dev_poses, dev_ranges, SCANS_DEV);
 }
 
 int b200nav_himm_last_stats(b200nav_grid* g, int64_t* out3) {

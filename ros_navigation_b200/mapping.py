@@ -141,6 +141,11 @@ class DeviceGridMap:
         check(lib().b200nav_himm_update_scans_batched(self.h, layer.encode(), info.ctypes.data, poses.ctypes.data,
                                                       ranges.ctypes.data), self.ctx.h)
 
+    def himm_update_scans_batched_async(self, layer, info, host_poses, host_ranges):
+        """Enqueue-only form: pinned host buffers that stay valid until the context caught up."""
+        check(lib().b200nav_himm_update_scans_batched_async(self.h, layer.encode(), info.ctypes.data, ptr(host_poses),
+                                                            ptr(host_ranges)), self.ctx.h)
+
     def himm_update_scans_batched_dev(self, layer, info, dev_poses, dev_ranges):
         check(lib().b200nav_himm_update_scans_batched_dev(self.h, layer.encode(), info.ctypes.data, ptr(dev_poses),
                                                           ptr(dev_ranges)), self.ctx.h)

@@ -101,7 +101,11 @@ def test_scan_form_update_matches_oracle(beams, fov, decimate):
         ranges = rng.uniform(0.1, 7.0, (n_robots, beams)).astype(np.float32)   # some below min, some beyond max
         ranges[:, ::97] = np.inf
         ranges[1, 5] = np.nan
-        if cycle % 2 == 0:
+        if cycle == 2:   # enqueue-only form from pinned host buffers
+            hp, hr = torch.from_numpy(poses).pin_memory(), torch.from_numpy(ranges).pin_memory()
+            dg.himm_update_scans_batched_async("laser", info, hp, hr)
+            ctx.synchronize()
+        elif cycle % 2 == 0:
             dg.himm_update_scans_batched("laser", info, poses, ranges)
         else:
             dg.himm_update_scans_batched_dev("laser", info, torch.from_numpy(poses).cuda(), torch.from_numpy(ranges).cuda())
