@@ -6,17 +6,21 @@
  * LaserMapUpdater::updateMap (move_control/src/laser_map_updater.cpp:15-20) and grid_map::LineIterator
  * (grid_map_core/src/iterators/LineIterator.cpp:16-150).
  *
- * Design (see DESIGN.md "HIMM"):
- *   K0 himm_prep_kernel   one thread per RangeSample: fp64 clip of both ray ends into the map and
- *                         position->index, producing a 24-byte BeamSeg (integer Bresenham end points + mark cell).
- *   K1 himm_tile_kernel   one CTA per (grid tile, robot).  A tile is split into SUB x SUB sub-tiles, each OWNED by
- *                         one warp and staged in shared memory.  The owning warp applies every beam that crosses its
- *                         sub-tile strictly in sample order (clear along the Bresenham cells, then the +30 mark),
- *                         32 lanes striding over the cells of ONE beam through a closed form of the Bresenham
- *                         recurrence.  Because a cell is only ever touched by its owner warp, in order, no atomics
- *                         are needed and the saturating clear/mark sequence is reproduced bit-exactly - the result
- *                         cannot depend on scheduling.  Only the 256-byte column segments a beam actually crosses
- *                         are loaded from / stored to HBM (coalesced, full sectors).
+ * Design:
+ *   K0 himm_prep_kernel        one thread per RangeSample (or cloud point, or raw scan reading): fp64 clip of both ray
+ *                              ends into the map and position->index, producing a 24-byte BeamSeg (integer Bresenham
+ *                              end points + mark cell); then every 64 x 64 tile the line touches gets the beam's bit
+ *                              in the tile's beam mask, and every tile touched for the first time is appended to the
+ *                              work list.
+ *   K1 himm_tile_coded_kernel  persistent one-warp CTAs pull (robot, tile) work items.  The warp OWNS the tile: the
+ *                              byte-coded tile record (cells.cuh) is staged in shared memory by one bulk async copy,
+ *                              every beam of the tile's mask is applied strictly in sample order (clear along the
+ *                              Bresenham cells, then the +30 mark), 32 beams at a time in lock step over the step
+ *                              index, and the record is copied back.  Because a cell is only ever touched by its owner
+ *                              warp, in order, no atomics are needed and the saturating clear / mark sequence is
+ *                              reproduced bit-exactly - the result cannot depend on scheduling.
+ *      himm_tile_kernel        the same walk for float layers (float4 staging with encode / decode; tiles holding
+ *                              values outside the HIMM set are processed in place).
  */
 #ifndef B200NAV_HIMM_KERNELS_CUH
 #define B200NAV_HIMM_KERNELS_CUH

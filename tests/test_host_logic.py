@@ -64,3 +64,26 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("oracle restatement", ""), os.path.join(dirpath, f)
+
+
+def test_host_only_entry_points_validate_arguments():
+    """Entry points that do not need a device reject bad arguments with B200NAV_EINVAL instead of crashing (no GPU
+    needed: nothing is launched)."""
+    import ctypes as C
+    import numpy as np
+    from ros_navigation_b200 import capi
+    L = capi.lib()
+    assert L.b200nav_scan_select(None, None, 0, None) == capi.EINVAL
+    info = np.zeros(1, capi.SCAN_INFO_DTYPE)
+    info["n_ranges"] = -1
+    assert L.b200nav_scan_select(info.ctypes.data, None, 0, None) == capi.EINVAL
+    assert L.b200nav_fleet_unique_id(None) == capi.EINVAL
+    h = C.c_void_p()
+    assert L.b200nav_fleet_create(None, None, 0, 1, C.byref(h)) == capi.EINVAL
+    assert L.b200nav_fleet_wait(None, 0) == capi.EINVAL
+    assert L.b200nav_fleet_gather_async(None, 0, None, None, 0) == capi.EINVAL
+    assert L.b200nav_fleet_destroy(None) == capi.OK
+    assert L.b200nav_ctx_flush_l2(None, 0, 0) == capi.EINVAL
+    assert L.b200nav_ctx_fence(None, None) == capi.EINVAL and L.b200nav_ctx_wait(None, 0) == capi.EINVAL
+    assert L.b200nav_himm_update_scans_batched(None, b"laser", None, None, None) == capi.EINVAL
+    assert L.b200nav_grid_has_layer(None, b"x") == 0
