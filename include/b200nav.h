@@ -92,6 +92,12 @@ int b200nav_grid_add_layer(b200nav_grid* grid, const char* name);
 int b200nav_grid_alias_layer(b200nav_grid* grid, const char* alias, const char* target);
 /* map_[dst] = map_[src] for all robots (map_provider.cpp:221, the copying form). */
 int b200nav_grid_copy_layer(b200nav_grid* grid, const char* dst, const char* src);
+/* The two-layer compose that MapProvider::composeMasterMapFromLayerdMap carries commented out
+ * (move_control/src/map_provider.cpp:218-220): dst = (range is NaN and laser is not ? 0 : range) +
+ * (laser is NaN and range is not ? 0 : laser), all robots.  The destination becomes a FLOAT-format layer (sums leave
+ * the HIMM value set) and must not alias a source.  Asynchronous on the context's stream.  The compose the reference
+ * actually runs (master = laser, :221) is b200nav_grid_copy_layer / b200nav_grid_alias_layer. */
+int b200nav_grid_compose_master(b200nav_grid* grid, const char* dst, const char* range_layer, const char* laser_layer);
 /* GridMap::clear(layer) / clearAll (GridMap.cpp:605-629): NaN fill.  layer == NULL clears every layer. */
 int b200nav_grid_clear(b200nav_grid* grid, const char* layer);
 /* Whole-layer transfer for one robot; `colmajor` is rows*cols floats laid out like Eigen::MatrixXf::data(). */

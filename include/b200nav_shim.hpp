@@ -73,6 +73,13 @@ class GridLayers {
   int aliasLayer(const std::string& alias, const std::string& target) {
     return b200nav_grid_alias_layer(grid_, alias.c_str(), target.c_str());
   }
+  /* the two-layer compose the reference carries commented out (map_provider.cpp:218-220) */
+  int composeMaster(const std::string& dst = "master", const std::string& range_layer = "range",
+                    const std::string& laser_layer = "laser") {
+    return b200nav_grid_compose_master(grid_, dst.c_str(), range_layer.c_str(), laser_layer.c_str());
+  }
+  /* true while the layer lives on the device as one byte per cell (see b200nav_grid_layer_format) */
+  bool isCoded(const std::string& layer) { return b200nav_grid_layer_format(grid_, layer.c_str()) == B200NAV_LAYER_CODED; }
   /* Eigen::MatrixXf-compatible transfer: column-major rows x cols floats (grid_map::Matrix::data()) */
   int upload(const std::string& layer, const float* colmajor, int robot = 0) {
     return b200nav_grid_upload(grid_, robot, layer.c_str(), colmajor);

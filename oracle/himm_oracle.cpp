@@ -663,4 +663,15 @@ int oracle_project_scan(float angle_min, float increment_used, float range_min, 
   return n;
 }
 
+void oracle_compose_master(const float* range, const float* laser, float* master, long long n) {
+  /* The compose MapProvider::composeMasterMapFromLayerdMap carries commented out (map_provider.cpp:218-220):
+   *   (range.isNaN() && !laser.isNaN()).select(0, range) + (laser.isNaN() && !range.isNaN()).select(0, laser) */
+  for (long long i = 0; i < n; i++) {
+    const bool range_nan = std::isnan(range[i]), laser_nan = std::isnan(laser[i]);
+    const float first = (range_nan && !laser_nan) ? 0.0f : range[i];
+    const float second = (laser_nan && !range_nan) ? 0.0f : laser[i];
+    master[i] = first + second;
+  }
+}
+
 } /* extern "C" */

@@ -69,6 +69,7 @@ def lib():
         L.oracle_to_occupancy.argtypes = [gp, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         L.oracle_goal_from_pose.argtypes = [C.c_double] * 5 + [_fp, _fp]
         L.oracle_if_blocked.argtypes = [gp, C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.oracle_compose_master.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
         L.oracle_sincos.argtypes = [C.c_double, _dp, _dp]
         L.oracle_scan_select.argtypes = [C.c_float, C.c_int, C.c_int, C.c_void_p, _fp]
         L.oracle_project_scan.argtypes = [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p] + [C.c_double] * 3 + [C.c_void_p]
@@ -196,6 +197,15 @@ def ranges_from_submap(g, master, rx, ry, yaw, submap_len=1.5):
     ranges = np.zeros((361, 2), dtype=np.float64)
     lib().oracle_ranges_from_submap(C.byref(g), master.ctypes.data, rx, ry, yaw, submap_len, ranges.ctypes.data)
     return ranges
+
+
+def compose_master(range_layer, laser_layer):
+    """master = range (+) laser (the commented-out compose, map_provider.cpp:218-220)."""
+    a = np.ascontiguousarray(range_layer, dtype=np.float32)
+    b = np.ascontiguousarray(laser_layer, dtype=np.float32)
+    out = np.empty_like(a)
+    lib().oracle_compose_master(a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size)
+    return out
 
 
 def sincos(x):

@@ -94,6 +94,9 @@ int oracle_if_blocked(const oracle_geom* g, const float* master, double x, doubl
 void oracle_goal_from_pose(double rx, double ry, double yaw, double tx, double ty,
                            float* desired_angle, float* desired_dist);
 
+/* The commented-out two-layer compose of MapProvider::composeMasterMapFromLayerdMap (map_provider.cpp:218-220). */
+void oracle_compose_master(const float* range, const float* laser, float* master, long long n);
+
 /* LaserScan -> RangeSamples: restatement of the specification in ros_navigation_b200/csrc/scan_project.h (intake side
  * of LaserMapUpdater::bufferIncomingMsg, laser_map_updater.cpp:38-144; laser_geometry / tf are not in the reference
  * tree: parity with the reference unpinned here). */

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "b200nav_fleet_gather_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200nav_fleet_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_fleet_destroy": (C.c_int, [C.c_void_p]),
+    "b200nav_grid_compose_master": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "b200nav_grid_has_layer": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_grid_layer_format": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_update": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -946,6 +946,31 @@ int b200nav_grid_copy_layer(b200nav_grid* g, const char* dst, const char* src) {
   return B200NAV_OK;
 }
 
+int b200nav_grid_compose_master(b200nav_grid* g, const char* dst, const char* range_layer, const char* laser_layer) {
+  if (!g) return B200NAV_EINVAL;
+  Layer *d = find_layer(g, dst), *a = find_layer(g, range_layer), *b = find_layer(g, laser_layer);
+  if (!d || !a || !b) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", !d ? dst : (!a ? range_layer : laser_layer));
+  if (d == a || d == b) return set_err(g->ctx, B200NAV_EINVAL, "compose: the destination must not alias a source layer");
+  b200nav_ctx* ctx = g->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  { int jrc = join_side(ctx); if (jrc) return jrc; }
+  if (d->coded) { /* sums leave the HIMM value set: the destination becomes a float layer (contents are overwritten) */
+    CUDA_TRY(ctx, sync_raw(ctx));
+    void* nd = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&nd, g->layer_elems() * sizeof(float)));
+    cudaFree(d->dev);
+    d->dev = nd;
+    d->coded = false;
+  }
+  int rc = reset_free_cols(g, d, -1);
+  if (rc) return rc;
+  const size_t per = (size_t)g->dims.rows * g->dims.cols;
+  grid_compose_kernel<<<conv_blocks(g, g->layer_elems(), 256), 256, 0, ctx->stream>>>(
+      layer_ref(g, a, 0), a->coded ? coded_robot_bytes(g) : per * sizeof(float), layer_ref(g, b, 0),
+      b->coded ? coded_robot_bytes(g) : per * sizeof(float), d->fdev(), g->dims.rows, g->dims.cols, g->layer_elems());
+  return check_launch(ctx, "grid_compose_kernel");
+}
+
 int b200nav_grid_clear(b200nav_grid* g, const char* layer) {
   if (!g) return B200NAV_EINVAL;
   { int jrc = join_side(g->ctx); if (jrc) return jrc; }

@@ -96,6 +96,27 @@ __global__ void grid_blocked_kernel(GridDims d, RobotGeom g, const LayerRef laye
   if (lane == 0) out[q] = any ? 1 : 0;
 }
 
+/* The two-layer compose MapProvider::composeMasterMapFromLayerdMap carries commented out
+ * (move_control/src/map_provider.cpp:218-220): master = (range is NaN and laser is not ? 0 : range) +
+ * (laser is NaN and range is not ? 0 : laser), i.e. the sum where both are known, the known one where only one is,
+ * NaN where neither is.  Sources in either layer format (one robot's LayerRef stride apart), destination float. */
+__global__ void grid_compose_kernel(LayerRef a, size_t a_stride, LayerRef b, size_t b_stride, float* __restrict__ dst,
+                                    int rows, int cols, size_t n_total) {
+  const size_t per = (size_t)rows * cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride) {
+    const size_t robot = i / per, lin = i - robot * per;
+    const int r = (int)(lin % rows), c = (int)(lin / rows);
+    LayerRef ar = a, br = b;
+    ar.base = static_cast<const char*>(a.base) + robot * a_stride;
+    br.base = static_cast<const char*>(b.base) + robot * b_stride;
+    const float x = ar.at(r, c), y = br.at(r, c);
+    const float x2 = (isnan(x) && !isnan(y)) ? 0.0f : x;
+    const float y2 = (isnan(y) && !isnan(x)) ? 0.0f : y;
+    dst[i] = x2 + y2;
+  }
+}
+
 /* Measurement aid (bench.py): stream `n16` 16-byte words through L2 - write them (mode 1), or read them and fold
  * the result into *sink (mode 2) - so that nothing of the previous step is left in the cache. */
 __global__ void l2_flush_kernel(uint4* __restrict__ buf, size_t n16, int mode, unsigned* __restrict__ sink) {

@@ -39,6 +39,11 @@ class DeviceGridMap:
         """map_[dst] = map_[src] (MapProvider::composeMasterMapFromLayerdMap, map_provider.cpp:221)."""
         check(lib().b200nav_grid_copy_layer(self.h, dst.encode(), src.encode()), self.ctx.h)
 
+    def compose_master(self, dst="master", range_layer="range", laser_layer="laser"):
+        """dst = range (+) laser as in the commented-out compose of map_provider.cpp:218-220."""
+        check(lib().b200nav_grid_compose_master(self.h, dst.encode(), range_layer.encode(), laser_layer.encode()),
+              self.ctx.h)
+
     def clear(self, layer=None):
         check(lib().b200nav_grid_clear(self.h, layer.encode() if layer else None), self.ctx.h)
 

@@ -131,3 +131,36 @@ def test_error_paths(ctx):
         DeviceGridMap(ctx, (4000.0, 4.0), 0.05)
     assert e.value.code == capi.ERANGE
     dg.close()
+
+
+def test_two_layer_compose_and_steering_from_it(ctx):
+    """the sonar ("range") layer merged into master with the compose the reference carries
+    commented out (map_provider.cpp:218-220); the VFH+ window then reads the composed (float-format) master."""
+    from ros_navigation_b200 import VFH, DeviceGridMap
+    from tests.util import random_samples
+    rng = np.random.default_rng(21)
+    g = O.make_geom(8.0, 8.0, 0.05)
+    dg = DeviceGridMap(ctx, (8.0, 8.0), 0.05, n_robots=2, layers=("master", "laser", "range"))
+    laser = [O.new_layer(g), O.new_layer(g)]
+    sonar = [O.new_layer(g), O.new_layer(g)]
+    v = VFH(ctx, n_robots=2)
+    for cycle in range(4):
+        per_l = [lidar_samples(rng, g, (0.2 * r, -0.3), 360, 0.3, 3.0) for r in range(2)]
+        per_s = [random_samples(rng, g, 25, spread=0.6, clear_frac=0.2, origin=(0.2 * r, -0.3)) for r in range(2)]
+        for per, name, store in ((per_l, "laser", laser), (per_s, "range", sonar)):
+            off = np.cumsum([0] + [len(p) for p in per]).astype(np.int32)
+            dg.himm_update_batched(name, np.concatenate(per), off)
+            for r in range(2):
+                O.himm_update(g, store[r], per[r])
+        dg.compose_master("master", "range", "laser")
+    assert dg.layer_format("master") == "float" and dg.layer_format("laser") == "coded"
+    for r in range(2):
+        want = O.compose_master(sonar[r], laser[r])
+        assert_layers_equal(dg.download("master", robot=r), want, "master of robot %d" % r)
+        pose = (0.2 * r, -0.3, 0.4)
+        v.update_from_grid(dg, "master", VFH.make_input(x=pose[0], y=pose[1], yaw=pose[2]), robot=r)
+        assert np.array_equal(v.ranges(robot=r)[:, 0], O.ranges_from_submap(g, want, *pose)[:, 0])
+    with pytest.raises(Exception):
+        dg.compose_master("laser", "range", "laser")      # destination aliases a source
+    v.close()
+    dg.close()
