@@ -162,7 +162,11 @@ class CpuArm:
         self.cfg = cfg = cyc.cfg
         self.geom = O.make_geom(cfg["extent"], cfg["extent"], cfg["res"])
         self.layers = [O.new_layer(self.geom) for _ in range(n_robots)]
-        self.kind = "port+reference" if O.have_ref() else "port"
+        # HIMM / pseudo-scan: the oracle's restatement (the reference's grid_map / ROS side does not build here);
+        # VFH+: the unmodified reference vfh.cpp when oracle/_ref is present.  Reported as "port" (the weaker claim).
+        self.kind = "port"
+        self.parts = ("HIMM + pseudo-scan: oracle restatement; VFH+: " +
+                      ("unmodified reference vfh.cpp" if O.have_ref() else "not run (oracle/_ref missing)"))
         self.vfh = None
         if O.have_ref():
             self.vfh = [O.RefVFH(window_diameter=cfg["window"], cell_size=cfg["cell"]) for _ in range(n_robots)]
@@ -220,7 +224,7 @@ def run_reference_arm(args, rank, world):
     for k in range(args.steps):
         secs += arm.run_cycle(args.warmup + k)
     value = arm.n * args.steps / secs
-    sample = "%d robots x %d cycles of workload %s per run" % (arm.n, args.steps, args.workload)
+    sample = "%d robots x %d cycles of workload %s per run; %s" % (arm.n, args.steps, args.workload, arm.parts)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
@@ -525,7 +529,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             n_cyc = int(max(2, min(2000, 12.0 / max(t_cal, 1e-3))))
             secs = sum(cpu.run_cycle(1 + k) for k in range(n_cyc))
             line["cpu_baseline"] = {"value": cpu.n * n_cyc / secs, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
-                                    "sample": "%d robots x %d cycles of workload %s (%.1f s)" % (
+                                    "sample": ("%d robots x %d cycles of workload %s (%.1f s); " + cpu.parts) % (
                                         cpu.n, n_cyc, args.workload, secs)}
         except Exception as e:  # the baseline must never take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
