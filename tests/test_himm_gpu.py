@@ -359,6 +359,58 @@ def test_async_cycles_overlap_and_match_synchronous_calls(ctx):
         x.close()
 
 
+def test_long_steady_state_fleet_sequence(ctx):
+    """150 cycles of the bench's own synthetic workload (rooms with discs and boxes, 1080-beam noisy scans along
+    Lissajous paths) for a small fleet: walls saturate, free space is re-cleared every cycle, marks and clears keep
+    meeting in the same cells - the steady state the throughput numbers are measured in.  Grids bit-exact against the
+    oracle half way and at the end; the closed loop (HIMM -> window -> VFH+) equals oracle + reference VFH throughout."""
+    import torch
+    from ros_navigation_b200 import VFH, DeviceGridMap, synth
+    n, cycles, beams, rmax = 6, 150, 1080, 6.0
+    W = synth.Worlds(n, 12.8, seed=4242)
+    g = O.make_geom(12.8, 12.8, 0.05)
+    dg = DeviceGridMap(ctx, (12.8, 12.8), 0.05, n_robots=n, layers=("laser",))
+    dg.alias("master", "laser")
+    layers = [O.new_layer(g) for _ in range(n)]
+    have_ref = O.have_ref()
+    refs = [O.RefVFH() for _ in range(n)] if have_ref else None
+    v = VFH(ctx, n_robots=n)
+    speeds = np.zeros(n, np.int32)
+    for c in range(cycles):
+        t = 0.2 * c
+        x, y, yaw = W.pose(t)
+        r, ang = W.cast(x, y, yaw, beams, 1.5 * np.pi, rmax)
+        org, xy, clr, off = synth.cloud_from_scan(x, y, yaw, r, ang, rmax, keep_max=(c % 7 == 3))
+        dg.himm_update_cloud_batched("laser", org.numpy(), xy.numpy(), clr.numpy(), off.numpy())
+        offs = off.numpy()
+        for k in range(n):
+            sl = slice(offs[k], offs[k + 1])
+            cnt = offs[k + 1] - offs[k]
+            O.himm_update(g, layers[k], O.make_samples(np.full(cnt, float(x[k])), np.full(cnt, float(y[k])),
+                                                       xy[sl, 0].double().numpy(), xy[sl, 1].double().numpy(),
+                                                       clr[sl].numpy()))
+        inp = synth.vfh_inputs_to_numpy(synth.vfh_inputs(W, t, 0.2, torch.from_numpy(speeds)))
+        out = v.update_batched(dg, "master", inp)
+        if have_ref and c % 5 == 0:
+            for k in range(n):
+                want_r = O.ranges_from_submap(g, layers[k], inp["x"][k], inp["y"][k], inp["yaw"][k])
+                rcs, rct = refs[k].update(want_r, int(speeds[k]), float(inp["goal_direction"][k]),
+                                          float(inp["goal_distance"][k]), 250.0, 0.2)
+                assert (int(out["speed"][k]), int(out["turnrate"][k])) == (rcs, rct), "cycle %d robot %d" % (c, k)
+        elif have_ref:
+            for k in range(n):   # keep the reference's state (hysteresis, last picked angle, speed) in step
+                refs[k].update(O.ranges_from_submap(g, layers[k], inp["x"][k], inp["y"][k], inp["yaw"][k]),
+                               int(speeds[k]), float(inp["goal_direction"][k]), float(inp["goal_distance"][k]), 250.0, 0.2)
+        speeds = out["speed"].astype(np.int32).copy()
+        if c in (cycles // 2, cycles - 1):
+            for k in range(n):
+                assert_layers_equal(dg.download("laser", robot=k), layers[k], "cycle %d robot %d" % (c, k))
+    sat = sum(int((np.nan_to_num(l) >= 150).sum()) for l in layers)
+    assert sat > 200, "the sequence should reach saturated wall cells (%d)" % sat
+    v.close()
+    dg.close()
+
+
 def test_c2_sized_grid_scan_sequence(ctx):
     """BASELINE config 2 geometry: 2048 x 2048 @ 5 cm, 1080-beam / 270 deg scans up to 30 m."""
     import torch
