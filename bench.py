@@ -267,7 +267,8 @@ class GpuArm:
         self.vfh = VFH(self.ctx, VfhParams(window_diameter=cfg["window"], cell_size=cfg["cell"],
                                            submap_length=cfg["submap"]), n_robots=self.n)
         from ros_navigation_b200.dist import CommandExchange
-        self.exchange = (CommandExchange(robots_total, device, ctx=None if os.environ.get("B200NAV_TORCH_EXCHANGE") else self.ctx)
+        self.exchange = (CommandExchange(robots_total, device, ctx=None if os.environ.get("B200NAV_TORCH_EXCHANGE") else self.ctx,
+                                         peer_push=bool(os.environ.get("B200NAV_PEER_PUSH")))
                          if (world > 1 and not os.environ.get("B200NAV_BENCH_NO_EXCHANGE")) else None)
         self.cmd = self.exchange.local if self.exchange else torch.zeros(self.n, 16, dtype=torch.uint8, device=device)
         self.gathered = self.exchange.table if self.exchange else None
@@ -299,9 +300,12 @@ class GpuArm:
             self.vfh.update_batched_dev(self.grid, "master", self.cyc.inputs[c], self.cmd)
             return
         slot = i & 1
-        self.exchange.wait(slot)  # the gather that last read this buffer has finished
-        self.vfh.update_batched_dev(self.grid, "master", self.cyc.inputs[c], self.exchange.locals[slot])
-        self.exchange.gather_async(slot)
+        if self.exchange.push:  # fused: the VFH+ kernel stores the commands into every rank's table itself
+            self.exchange.vfh_update_push(self.vfh, self.grid, "master", self.cyc.inputs[c], slot)
+        else:
+            self.exchange.wait(slot)  # the gather that last read this buffer has finished
+            self.vfh.update_batched_dev(self.grid, "master", self.cyc.inputs[c], self.exchange.locals[slot])
+            self.exchange.gather_async(slot)
         if last:
             self.exchange.wait()
 
@@ -347,10 +351,13 @@ class GpuArm:
                 self.vfh.update_batched_async(self.grid, "master", self.h_inputs[c], self.h_cmds[slot])
             else:
                 self.d_inputs_e2e.copy_(self.h_inputs[c], non_blocking=True)
-                self.exchange.wait(slot)
-                self.vfh.update_batched_dev(self.grid, "master", self.d_inputs_e2e, self.exchange.locals[slot])
-                self.exchange.gather_async(slot)
-                self.exchange.wait(slot)  # stream-side wait: the copy below follows the gather
+                if self.exchange.push:
+                    self.exchange.vfh_update_push(self.vfh, self.grid, "master", self.d_inputs_e2e, slot)
+                else:
+                    self.exchange.wait(slot)
+                    self.vfh.update_batched_dev(self.grid, "master", self.d_inputs_e2e, self.exchange.locals[slot])
+                    self.exchange.gather_async(slot)
+                self.exchange.wait(slot)  # stream-side wait: the copy below follows the exchange
                 self.h_cmds[slot].copy_(self.exchange.tables[slot], non_blocking=True)
             tickets.append(self.ctx.fence())
             if k >= depth:
@@ -506,6 +513,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                                "vfh_update": vfh_ms / max(vfh_n, 1)},
         "wall_s_timed_region": wall,
         "host_enqueue_ms_per_step": getattr(arm, "host_enqueue_ms_per_step", None),
+        "exchange": (None if arm.exchange is None else
+                     ("peer push fused into the VFH+ kernel (NVLink P2P stores)" if arm.exchange.push else
+                      ("NCCL all-gather, library binding" if arm.exchange.fleet is not None else
+                       "torch.distributed all-gather"))),
     }
     # the two smaller kernels against the same HBM peak (SURVEY section 8d accounting; both are latency bound)
     beams = float(np.mean([u[3] for u in used]))

@@ -154,6 +154,16 @@ int b200nav_fleet_gather_async(b200nav_fleet* fleet, int slot, const void* dev_l
                                size_t bytes_per_rank);
 /* slot < 0: both slots. */
 int b200nav_fleet_wait(b200nav_fleet* fleet, int slot);
+/* Fused exchange ("peer push", optional): instead of a collective after the VFH+ update, the VFH+ kernel itself
+ * stores every robot's command into row (row0 + robot) of the table of EVERY rank through NVLink peer mappings and
+ * then publishes the cycle's epoch in every rank's flag array; b200nav_fleet_wait(slot) enqueues a small kernel that
+ * waits (bounded, about a second) for all ranks' epochs, after which b200nav_fleet_table(slot) holds the whole fleet.
+ * Setup: every rank calls _push_region (allocates its table + flags and returns a 64-byte CUDA IPC handle), the
+ * launcher all-gathers the handles, every rank calls _push_connect with all of them (rank order).  Contract as
+ * above: b200nav_fleet_wait(slot) before the update that writes slot again; at most one cycle per slot in flight. */
+int b200nav_fleet_push_region(b200nav_fleet* fleet, int n_local, int n_total, int row0, uint8_t* handle64);
+int b200nav_fleet_push_connect(b200nav_fleet* fleet, const uint8_t* handles);
+void* b200nav_fleet_table(b200nav_fleet* fleet, int slot);
 int b200nav_fleet_destroy(b200nav_fleet* fleet);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -325,6 +335,11 @@ int b200nav_vfh_update_batched_async(b200nav_vfh* vfh, b200nav_grid* grid, const
 /* Same with device arrays; asynchronous. */
 int b200nav_vfh_update_batched_dev(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
                                    const b200nav_vfh_input* dev_in, b200nav_command* dev_out);
+
+/* Batched update whose kernel also delivers the commands to every rank (see b200nav_fleet_push_region); device
+ * inputs, asynchronous.  The fleet's n_local must equal the robot count of vfh and grid. */
+int b200nav_vfh_update_batched_dev_push(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
+                                        const b200nav_vfh_input* dev_in, b200nav_fleet* fleet, int slot);
 
 /* Read back per-robot state after an update (any pointer may be NULL):
  *  origin_hist / hist / last_binary: hist_size floats (VFH::OriginHist, VFH::Hist, Last_Binary_Hist);

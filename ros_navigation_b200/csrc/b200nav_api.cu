@@ -169,6 +169,27 @@ struct b200nav_fleet {
   cudaStream_t stream = nullptr;
   cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
   bool pending[2] = {false, false};
+  /* peer push (fused exchange): one IPC-shared region per rank = [2 slots][n_total commands] + [2 slots][world] flags
+   * + a block counter + an error word */
+  bool push = false;
+  int n_local = 0, n_total = 0, row0 = 0;
+  uint8_t* region = nullptr;
+  size_t region_bytes = 0;
+  uint8_t* peer_region[B200NAV_MAX_PEERS] = {nullptr};
+  unsigned long long epoch[2] = {0, 0};
+  bool push_pending[2] = {false, false};
+  b200nav_command* table(int p, int slot) const {
+    return reinterpret_cast<b200nav_command*>(peer_region[p]) + (size_t)slot * n_total;
+  }
+  unsigned long long* flags(int p, int slot) const {
+    return reinterpret_cast<unsigned long long*>(peer_region[p] + sizeof(b200nav_command) * 2 * (size_t)n_total) +
+           (size_t)slot * world;
+  }
+  unsigned int* counter() const {
+    return reinterpret_cast<unsigned int*>(region + sizeof(b200nav_command) * 2 * (size_t)n_total +
+                                           sizeof(unsigned long long) * 2 * (size_t)world);
+  }
+  int* errword() const { return reinterpret_cast<int*>(counter() + 1); }
 };
 
 struct b200nav_vfh {
@@ -596,9 +617,13 @@ size_t vfh_smem_bytes(const b200nav_vfh* v, bool from_grid, int box_r, int box_c
 }
 
 int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const Layer* layer, const b200nav_vfh_input* dev_in,
-               const double* dev_ranges, b200nav_command* dev_out, int robot0, int n, cudaStream_t stream = nullptr) {
+               const double* dev_ranges, b200nav_command* dev_out, int robot0, int n, cudaStream_t stream = nullptr,
+               const VfhPush* push_in = nullptr) {
   b200nav_ctx* ctx = v->ctx;
   if (!stream) stream = ctx->stream;
+  VfhPush push;
+  memset(&push, 0, sizeof(push));
+  if (push_in) push = *push_in;
   VfhGridArgs ga;
   memset(&ga, 0, sizeof(ga));
   CUtensorMap tm;
@@ -622,12 +647,12 @@ int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const Layer* layer, const b200na
     if (smem > (size_t)kVfhMaxSmem) return set_err(ctx, B200NAV_ERANGE, "VFH window too large for shared memory (%zu B)", smem);
     auto kern = vfh_update_kernel<true>;
     ProfScope ps(ctx, PROF_VFH, stream);
-    kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, nullptr, dev_out, robot0);
+    kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, nullptr, dev_out, robot0, push);
   } else {
     smem = vfh_smem_bytes(v, false, 0, 0);
     auto kern = vfh_update_kernel<false>;
     ProfScope ps(ctx, PROF_VFH, stream);
-    kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, dev_ranges, dev_out, robot0);
+    kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, dev_ranges, dev_out, robot0, push);
   }
   return check_launch(ctx, "vfh_update_kernel");
 }
@@ -1280,6 +1305,13 @@ int b200nav_fleet_gather_async(b200nav_fleet* f, int slot, const void* dev_local
 int b200nav_fleet_wait(b200nav_fleet* f, int slot) {
   if (!f || slot > 1) return B200NAV_EINVAL;
   for (int s = (slot < 0 ? 0 : slot); s <= (slot < 0 ? 1 : slot); s++)
+    if (f->push_pending[s]) { /* peer push: wait (on the stream) until every rank has published this slot's epoch */
+      fleet_wait_kernel<<<1, 32, 0, f->ctx->stream>>>(f->flags(f->rank, s), f->world, f->epoch[s], f->errword());
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return set_err(f->ctx, B200NAV_ECUDA, "fleet_wait_kernel: %s", cudaGetErrorString(e));
+      f->push_pending[s] = false;
+    }
+  for (int s = (slot < 0 ? 0 : slot); s <= (slot < 0 ? 1 : slot); s++)
     if (f->pending[s]) { /* stream-side wait: later work on the context's stream sees the gathered table */
       CUDA_TRY(f->ctx, cudaStreamWaitEvent(f->ctx->stream, f->done[s], 0));
       f->pending[s] = false;
@@ -1287,9 +1319,83 @@ int b200nav_fleet_wait(b200nav_fleet* f, int slot) {
   return B200NAV_OK;
 }
 
+int b200nav_fleet_push_region(b200nav_fleet* f, int n_local, int n_total, int row0, uint8_t* handle64) {
+  if (!f || !handle64 || n_local < 1 || n_total < n_local || row0 < 0 || row0 + n_local > n_total ||
+      f->world > B200NAV_MAX_PEERS)
+    return B200NAV_EINVAL;
+  b200nav_ctx* ctx = f->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  f->n_local = n_local;
+  f->n_total = n_total;
+  f->row0 = row0;
+  f->region_bytes = sizeof(b200nav_command) * 2 * (size_t)n_total + sizeof(unsigned long long) * 2 * (size_t)f->world + 16;
+  CUDA_TRY(ctx, cudaMalloc((void**)&f->region, f->region_bytes));
+  CUDA_TRY(ctx, cudaMemset(f->region, 0, f->region_bytes));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, f->region));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return B200NAV_OK;
+}
+
+int b200nav_fleet_push_connect(b200nav_fleet* f, const uint8_t* handles) {
+  if (!f || !handles || !f->region) return B200NAV_EINVAL;
+  b200nav_ctx* ctx = f->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int p = 0; p < f->world; p++) {
+    if (p == f->rank) {
+      f->peer_region[p] = f->region;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)p, 64);
+    void* ptr = nullptr;
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    f->peer_region[p] = static_cast<uint8_t*>(ptr);
+  }
+  f->push = true;
+  return B200NAV_OK;
+}
+
+void* b200nav_fleet_table(b200nav_fleet* f, int slot) {
+  if (!f || !f->region || slot < 0 || slot > 1) return nullptr;
+  return reinterpret_cast<b200nav_command*>(f->region) + (size_t)slot * f->n_total;
+}
+
+int b200nav_vfh_update_batched_dev_push(b200nav_vfh* v, b200nav_grid* g, const char* layer,
+                                        const b200nav_vfh_input* dev_in, b200nav_fleet* f, int slot) {
+  if (!v || !g || !dev_in || !f || slot < 0 || slot > 1) return B200NAV_EINVAL;
+  if (!f->push) return set_err(v->ctx, B200NAV_EINVAL, "fleet has no peer mappings (b200nav_fleet_push_connect)");
+  if (g->n_robots != v->n_robots || v->n_robots != f->n_local)
+    return set_err(v->ctx, B200NAV_EINVAL, "grid, vfh and fleet robot counts differ");
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(v->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  b200nav_ctx* ctx = v->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  { int jrc = join_side(ctx); if (jrc) return jrc; }
+  CUDA_TRY(ctx, v->out_buf.reserve(sizeof(b200nav_command) * (size_t)v->n_robots));
+  VfhPush push;
+  memset(&push, 0, sizeof(push));
+  for (int p = 0; p < f->world; p++) {
+    push.tables[p] = f->table(p, slot);
+    push.flags[p] = f->flags(p, slot);
+  }
+  push.world = f->world;
+  push.rank = f->rank;
+  push.row0 = f->row0;
+  push.epoch = ++f->epoch[slot];
+  push.done = f->counter();
+  f->push_pending[slot] = true;
+  return vfh_launch(v, g, l, dev_in, nullptr, static_cast<b200nav_command*>(v->out_buf.p), 0, v->n_robots, nullptr, &push);
+}
+
 int b200nav_fleet_destroy(b200nav_fleet* f) {
   if (!f) return B200NAV_OK;
   cudaSetDevice(f->ctx->device);
+  sync_raw(f->ctx);
+  for (int p = 0; p < f->world; p++)
+    if (p != f->rank && f->peer_region[p]) cudaIpcCloseMemHandle(f->peer_region[p]);
+  if (f->region) cudaFree(f->region);
   if (f->stream) cudaStreamSynchronize(f->stream);
   if (f->comm && f->CommDestroy) f->CommDestroy(f->comm);
   for (int i = 0; i < 2; i++) {

@@ -529,7 +529,7 @@ template <int SUB, int LIST_CAP>
 __global__ void __launch_bounds__(32, 30) himm_tile_kernel(HimmArgs a) {
   using Cfg = HimmTileCfg<SUB, LIST_CAP>;
   static_assert(SUB == HIMM_TILE && LIST_CAP == HIMM_CHUNK, "tile / chunk constants");
-  extern __shared__ __align__(16) unsigned char himm_smem_raw[];
+  extern __shared__ __align__(128) unsigned char himm_smem_raw[];
   uint8_t* tile = himm_smem_raw;
   uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + Cfg::kTileBytes); /* a.chunk_beams entries */
 

@@ -66,6 +66,20 @@ struct VfhGridArgs {
   int use_tma;
 };
 
+/* Fused command exchange ("peer push"): in the batched multi-GPU mode the kernel that takes the steering decision
+ * also delivers it - thread 0 of every block stores the robot's 16-byte command straight into row (row0 + block) of
+ * the command table of EVERY rank through NVLink peer mappings, and the last block to finish publishes the cycle's
+ * epoch in every rank's flag array (release: __threadfence_system before the counter, system-scope flag stores).
+ * The consumer side is fleet_wait_kernel.  world == 0: no exchange. */
+#define B200NAV_MAX_PEERS 16
+struct VfhPush {
+  b200nav_command* tables[B200NAV_MAX_PEERS]; /* table of rank p for this slot (peer-mapped)      */
+  unsigned long long* flags[B200NAV_MAX_PEERS]; /* flag array of rank p for this slot: [world]     */
+  int world, rank, row0;
+  unsigned long long epoch;
+  unsigned int* done; /* local block counter, zero between launches */
+};
+
 #define B200NAV_VFH_THREADS 128
 #define B200NAV_VFH_MAX_SECTORS 384 /* 360 / sector_angle, sector_angle >= 1 */
 #define B200NAV_NRANGES 361
@@ -144,7 +158,7 @@ template <bool FROM_GRID>
 __global__ void __launch_bounds__(B200NAV_VFH_THREADS)
 vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ CUtensorMap tmap,
                   const b200nav_vfh_input* __restrict__ in, const double* __restrict__ dev_ranges,
-                  b200nav_command* __restrict__ out, int robot0) {
+                  b200nav_command* __restrict__ out, int robot0, const VfhPush push) {
   extern __shared__ __align__(128) unsigned char vfh_smem_raw[];
   const VfhConst& c = v.c;
   const int H = c.hist_size, W = c.window, nf = v.nf;
@@ -608,8 +622,40 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
     cmd.picked_angle = st.picked;
     cmd.flags = flags;
     out[blockIdx.x] = cmd;
+    if (push.world > 0) {
+      const uint4 rec = make_uint4((unsigned)cmd.speed, (unsigned)cmd.turnrate, __float_as_uint(cmd.picked_angle), cmd.flags);
+      for (int p = 0; p < push.world; p++)
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&push.tables[p][push.row0 + blockIdx.x]),
+                     "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w)
+                     : "memory");
+      __threadfence_system();
+      if (atomicAdd(push.done, 1u) == gridDim.x - 1) { /* every block's rows are on their way: publish the epoch */
+        *push.done = 0u;
+        __threadfence_system();
+        for (int p = 0; p < push.world; p++)
+          *reinterpret_cast<volatile unsigned long long*>(&push.flags[p][push.rank]) = push.epoch;
+      }
+    }
     VFH_CLK(5); /* stage S */
   }
+}
+
+/* Consumer side of the peer push: one thread per rank waits (bounded) until that rank has published `epoch`.  Work
+ * enqueued after this kernel on the same stream sees the complete table. */
+__global__ void fleet_wait_kernel(const unsigned long long* flags, int world, unsigned long long epoch, int* err) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    const volatile unsigned long long* f = flags + r;
+    long long spins = 0;
+    while (*f < epoch) {
+      __nanosleep(200);
+      if (++spins > 5000000ll) { /* about a second: a peer died or never launched its update */
+        *err = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 }  // namespace b200nav

@@ -28,7 +28,7 @@ def owner_of(robot, total, world):
 class CommandExchange:
     """Per-cycle all-gather of the local robots' command records into a [total, 16] uint8 table."""
 
-    def __init__(self, total, device, group=None, ctx=None):
+    def __init__(self, total, device, group=None, ctx=None, peer_push=False):
         """ctx: a capi.Context.  When given (CUDA, world > 1, equal shares) the gathers go through the library's own
         NCCL binding (b200nav_fleet_*): a handful of driver calls per cycle instead of a torch.distributed collective,
         which matters when the host, not the GPU, is the bottleneck of a sub-millisecond cycle."""
@@ -47,8 +47,11 @@ class CommandExchange:
         self.tables = [torch.zeros(total, COMMAND_BYTES, dtype=torch.uint8, device=device) for _ in range(2)]
         self.local, self.table = self.locals[0], self.tables[0]
         self._pending = [None, None]
+        self.push = False
         if ctx is not None and self.world > 1 and self.even and torch.device(device).type == "cuda":
             self._init_fleet(device)
+            if peer_push:
+                self._init_push(device)
         if not self.even:  # padded staging so that every rank contributes the same number of bytes
             self._send = torch.zeros(self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
             self._recv = torch.zeros(self.world * self.max_local, COMMAND_BYTES, dtype=torch.uint8, device=device)
@@ -67,6 +70,37 @@ class CommandExchange:
         h = C.c_void_p()
         check(lib().b200nav_fleet_create(self.ctx.h, raw, self.rank, self.world, C.byref(h)), self.ctx.h)
         self.fleet = h
+
+    def _init_push(self, device):
+        """Fused exchange: the VFH+ kernel stores the commands into every rank's table over NVLink peer mappings
+        (b200nav_fleet_push_*); tables[slot] become views of the library's IPC-shared region."""
+        import ctypes as C
+        from .capi import check, lib
+        buf = (C.c_uint8 * 64)()
+        check(lib().b200nav_fleet_push_region(self.fleet, self.n_local, self.total, self.lo, buf), self.ctx.h)
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+        allh = torch.zeros(64 * self.world, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        raw = bytes(allh.cpu().tolist())
+        check(lib().b200nav_fleet_push_connect(self.fleet, raw), self.ctx.h)
+
+        class _View:  # minimal __cuda_array_interface__ holder
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n, COMMAND_BYTES), "typestr": "|u1", "data": (ptr, False),
+                                                 "version": 2, "strides": None}
+        self.tables = [torch.as_tensor(_View(lib().b200nav_fleet_table(self.fleet, s), self.total), device=device)
+                       for s in (0, 1)]
+        self.table = self.tables[0]
+        self.push = True
+
+    def vfh_update_push(self, vfh, grid, layer, dev_inputs, slot):
+        """The batched VFH+ update of this cycle with the exchange fused in; then wait(slot) before reading
+        tables[slot]."""
+        from .capi import check, lib, ptr
+        self.wait(slot)
+        check(lib().b200nav_vfh_update_batched_dev_push(vfh.h, grid.h, layer.encode(), ptr(dev_inputs), self.fleet, slot),
+              self.ctx.h)
+        self._pending[slot] = True
 
     def close(self):
         if self.fleet is not None:

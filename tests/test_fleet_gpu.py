@@ -41,6 +41,36 @@ with torch.cuda.stream(stream):
         assert torch.equal(a.tables[slot][lo:hi], a.locals[slot])
     assert torch.equal(a.gather(), a.tables[0])
     a.close()
+    # fused exchange: the VFH+ kernel pushes the commands into every rank's table (NVLink peer mappings)
+    import numpy as np
+    from ros_navigation_b200 import VFH, DeviceGridMap
+    n_local = 24
+    rng = np.random.default_rng(100 + rank)
+    push = CommandExchange(n_local * world, dev, ctx=ctx, peer_push=True)
+    plain = CommandExchange(n_local * world, dev, ctx=ctx)
+    assert push.push and not plain.push
+    grid = DeviceGridMap(ctx, (6.4, 6.4), 0.05, n_robots=n_local, layers=("master",))
+    lay = np.full((grid.cols, grid.rows), np.nan, np.float32)
+    for r in range(n_local):
+        m = rng.random(lay.shape)
+        l2 = lay.copy(); l2[m < 0.5] = 0.0; l2[m > 0.97] = 90.0
+        grid.upload("master", l2, robot=r)
+    va, vb = VFH(ctx, n_robots=n_local), VFH(ctx, n_robots=n_local)
+    for cycle in range(7):
+        slot = cycle & 1
+        inp = np.zeros(n_local, capi.VFH_INPUT_DTYPE)
+        inp["x"], inp["y"] = rng.uniform(-2, 2, n_local), rng.uniform(-2, 2, n_local)
+        inp["yaw"], inp["dt"], inp["current_speed"] = rng.uniform(-3, 3, n_local), 0.2, 100
+        inp["goal_direction"], inp["goal_distance"], inp["goal_tolerance"] = rng.uniform(0, 180, n_local), 2500.0, 250.0
+        d_in = torch.from_numpy(inp.view(np.uint8).reshape(n_local, -1)).to(dev)
+        push.vfh_update_push(va, grid, "master", d_in, slot)
+        plain.wait(slot)
+        vb.update_batched_dev(grid, "master", d_in, plain.locals[slot])
+        plain.gather_async(slot)
+        push.wait(slot); plain.wait(slot)
+        stream.synchronize()
+        assert torch.equal(push.tables[slot], plain.tables[slot]), (cycle, rank)
+    push.close(); plain.close()
 dist.barrier()
 dist.destroy_process_group()
 print("FLEET_OK", rank)
