@@ -1384,9 +1384,16 @@ int b200nav_vfh_update_batched_dev_push(b200nav_vfh* v, b200nav_grid* g, const c
   push.rank = f->rank;
   push.row0 = f->row0;
   push.epoch = ++f->epoch[slot];
-  push.done = f->counter();
   f->push_pending[slot] = true;
-  return vfh_launch(v, g, l, dev_in, nullptr, static_cast<b200nav_command*>(v->out_buf.p), 0, v->n_robots, nullptr, &push);
+  int rc = vfh_launch(v, g, l, dev_in, nullptr, static_cast<b200nav_command*>(v->out_buf.p), 0, v->n_robots, nullptr, &push);
+  if (rc) return rc;
+  /* the epoch goes out on the fleet's own stream, ordered after the update: off the main stream's critical path */
+  CUDA_TRY(ctx, cudaEventRecord(f->ready[slot], ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(f->stream, f->ready[slot], 0));
+  fleet_flag_kernel<<<1, 32, 0, f->stream>>>(push);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(ctx, B200NAV_ECUDA, "fleet_flag_kernel: %s", cudaGetErrorString(e));
+  return B200NAV_OK;
 }
 
 int b200nav_fleet_destroy(b200nav_fleet* f) {

@@ -67,18 +67,25 @@ struct VfhGridArgs {
 };
 
 /* Fused command exchange ("peer push"): in the batched multi-GPU mode the kernel that takes the steering decision
- * also delivers it - thread 0 of every block stores the robot's 16-byte command straight into row (row0 + block) of
- * the command table of EVERY rank through NVLink peer mappings, and the last block to finish publishes the cycle's
- * epoch in every rank's flag array (release: __threadfence_system before the counter, system-scope flag stores).
- * The consumer side is fleet_wait_kernel.  world == 0: no exchange. */
+ * also delivers it - thread 0 of every block stores the robot's 16-byte command straight into row (row0 + robot) of
+ * the command table of EVERY rank through NVLink peer mappings, overlapped with the other blocks' computation.
+ * fleet_flag_kernel (stream-ordered after the update, on the fleet's own stream) then publishes the cycle's epoch in
+ * every rank's flag array; the consumer side is fleet_wait_kernel.  world == 0: no exchange. */
 #define B200NAV_MAX_PEERS 16
 struct VfhPush {
   b200nav_command* tables[B200NAV_MAX_PEERS]; /* table of rank p for this slot (peer-mapped)      */
   unsigned long long* flags[B200NAV_MAX_PEERS]; /* flag array of rank p for this slot: [world]     */
   int world, rank, row0;
   unsigned long long epoch;
-  unsigned int* done; /* local block counter, zero between launches */
 };
+
+/* Runs after the VFH+ kernel of the cycle has completed (all its peer stores performed): tells every rank that this
+ * rank's rows of the slot are in place. */
+__global__ void fleet_flag_kernel(const VfhPush push) {
+  const int p = threadIdx.x;
+  __threadfence_system();
+  if (p < push.world) *reinterpret_cast<volatile unsigned long long*>(&push.flags[p][push.rank]) = push.epoch;
+}
 
 #define B200NAV_VFH_THREADS 128
 #define B200NAV_VFH_MAX_SECTORS 384 /* 360 / sector_angle, sector_angle >= 1 */
@@ -622,22 +629,17 @@ vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ 
     cmd.picked_angle = st.picked;
     cmd.flags = flags;
     out[blockIdx.x] = cmd;
-    if (push.world > 0) {
-      const uint4 rec = make_uint4((unsigned)cmd.speed, (unsigned)cmd.turnrate, __float_as_uint(cmd.picked_angle), cmd.flags);
-      for (int p = 0; p < push.world; p++)
-        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&push.tables[p][push.row0 + blockIdx.x]),
-                     "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w)
-                     : "memory");
-      __threadfence_system();
-      if (atomicAdd(push.done, 1u) == gridDim.x - 1) { /* every block's rows are on their way: publish the epoch */
-        *push.done = 0u;
-        __threadfence_system();
-        for (int p = 0; p < push.world; p++)
-          *reinterpret_cast<volatile unsigned long long*>(&push.flags[p][push.rank]) = push.epoch;
-      }
-    }
+    /* fused exchange (batched multi-GPU mode): the decision goes straight into row (row0 + robot) of every rank's
+     * command table through the NVLink peer mappings - plain stores, no fence: the epoch that tells the consumers the
+     * rows are complete is published by fleet_flag_kernel, stream-ordered after this kernel */
+    for (int p = 0; p < push.world; p++)
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&push.tables[p][push.row0 + blockIdx.x]),
+                   "r"((unsigned)cmd.speed), "r"((unsigned)cmd.turnrate), "r"(__float_as_uint(cmd.picked_angle)),
+                   "r"(cmd.flags)
+                   : "memory");
     VFH_CLK(5); /* stage S */
   }
+
 }
 
 /* Consumer side of the peer push: one thread per rank waits (bounded) until that rank has published `epoch`.  Work
