@@ -164,6 +164,8 @@ int b200nav_fleet_wait(b200nav_fleet* fleet, int slot);
 int b200nav_fleet_push_region(b200nav_fleet* fleet, int n_local, int n_total, int row0, uint8_t* handle64);
 int b200nav_fleet_push_connect(b200nav_fleet* fleet, const uint8_t* handles);
 void* b200nav_fleet_table(b200nav_fleet* fleet, int slot);
+/* Synchronises and reports (B200NAV_ERANGE) whether a wait of the peer push ran into its bound since the last call. */
+int b200nav_fleet_status(b200nav_fleet* fleet);
 int b200nav_fleet_destroy(b200nav_fleet* fleet);
 
 /* ------------------------------------------------------------------------------------------------------

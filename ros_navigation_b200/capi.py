@@ -87,6 +87,7 @@ _SIGNATURES = {
     "b200nav_fleet_push_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200nav_fleet_table": (C.c_void_p, [C.c_void_p, C.c_int]),
     "b200nav_vfh_update_batched_dev_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "b200nav_fleet_status": (C.c_int, [C.c_void_p]),
     "b200nav_fleet_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_fleet_destroy": (C.c_int, [C.c_void_p]),
     "b200nav_grid_compose_master": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]),

@@ -1396,6 +1396,23 @@ int b200nav_vfh_update_batched_dev_push(b200nav_vfh* v, b200nav_grid* g, const c
   return B200NAV_OK;
 }
 
+int b200nav_fleet_status(b200nav_fleet* f) {
+  if (!f) return B200NAV_EINVAL;
+  if (!f->region) return B200NAV_OK;
+  b200nav_ctx* ctx = f->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, sync_raw(ctx));
+  CUDA_TRY(ctx, cudaStreamSynchronize(f->stream));
+  int err = 0;
+  CUDA_TRY(ctx, cudaMemcpy(&err, f->errword(), sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    cudaMemset(f->errword(), 0, sizeof(int));
+    return set_err(ctx, B200NAV_ERANGE, "peer push: a rank did not publish its commands within the wait bound "
+                                        "(the table of that cycle is incomplete)");
+  }
+  return B200NAV_OK;
+}
+
 int b200nav_fleet_destroy(b200nav_fleet* f) {
   if (!f) return B200NAV_OK;
   cudaSetDevice(f->ctx->device);

@@ -102,6 +102,12 @@ class CommandExchange:
               self.ctx.h)
         self._pending[slot] = True
 
+    def status(self):
+        """Synchronise and raise if a peer-push wait timed out since the last call."""
+        if self.fleet is not None:
+            from .capi import check, lib
+            check(lib().b200nav_fleet_status(self.fleet), self.ctx.h)
+
     def close(self):
         if self.fleet is not None:
             from .capi import lib

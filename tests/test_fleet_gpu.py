@@ -70,6 +70,7 @@ with torch.cuda.stream(stream):
         push.wait(slot); plain.wait(slot)
         stream.synchronize()
         assert torch.equal(push.tables[slot], plain.tables[slot]), (cycle, rank)
+    push.status()
     push.close(); plain.close()
 dist.barrier()
 dist.destroy_process_group()
