@@ -580,7 +580,7 @@ def single_robot_numbers(device, name, scans=300):
     with torch.cuda.stream(stream):
         for k in range(50):
             arm.step_dev(k)
-    kms = {n: (lambda t: t[0] / max(t[1], 1))(arm.ctx.profile_read(n)) for n in ("himm_prep", "himm_tile", "vfh_update")}
+    kms = {n: arm.ctx.profile_read(n)[0] / 50.0 for n in ("himm_prep", "himm_tile", "vfh_update")}  # ms per scan
     arm.ctx.profile_enable(False)
     return {"workload": workload_config(name, 1, 1)["workload"], "value": scans / (dev_ms / 1000.0),
             "e2e": scans / e2e_s, "unit": UNIT, "ms_per_scan": dev_ms / scans, "kernel_ms": kms,

@@ -499,15 +499,34 @@ int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int 
   return check_launch(ctx, "himm_prep_kernel");
 }
 
-int himm_launch_tile(b200nav_grid* g, const HimmArgs& a) {
+constexpr int kHeavyWarps = 4; /* warps per CTA of the multi-warp heavy-tile kernel */
+
+int himm_launch_tile(b200nav_grid* g, const HimmArgs& a_in) {
   b200nav_ctx* ctx = g->ctx;
   int jrc = join_side(ctx); /* a VFH+ update on the side stream may still read the layer this kernel rewrites */
   if (jrc) return jrc;
+  HimmArgs a = a_in;
+  a.skip_heavy = 0;
+  const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
+  /* Experimental (B200NAV_MW_HEAVY=1): the tile that holds a scan's own origin sees every beam and keeps ONE warp
+   * busy for most of a single-robot update - give those items to CTAs of kHeavyWarps warps that split the rings of
+   * the tile among them; the one-warp kernel takes the rest.  Exact (tests/test_layer_formats_gpu.py runs the HIMM
+   * suite with it), but run back to back with the one-warp kernel it does not pay yet (C2: 0.079 ms instead of
+   * 0.057 ms for the tile phase): it needs its own stream next to the light items, see DESIGN.md section 7. */
+  static const char* mw_env = getenv("B200NAV_MW_HEAVY");
+  const bool use_mw = a.coded && mw_env && atoi(mw_env) != 0;
+  if (use_mw) {
+    ProfScope ps(ctx, PROF_HIMM_TILE);
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count);
+    himm_tile_coded_mw_kernel<kListCap, kHeavyWarps><<<blocks, 32 * kHeavyWarps, smem, ctx->stream>>>(a);
+    int rc = check_launch(ctx, "himm_tile_coded_mw_kernel");
+    if (rc) return rc;
+    a.skip_heavy = 1;
+  }
   /* persistent: as many one-warp CTAs as can be resident (32 per SM), never more than there are tiles */
   dim3 grid((unsigned)std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * 32));
   {
     ProfScope ps(ctx, PROF_HIMM_TILE);
-    const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
     if (a.coded) himm_tile_coded_kernel<kListCap><<<grid, TileCfg::kThreads, smem, ctx->stream>>>(a);
     else himm_tile_kernel<kSub, kListCap><<<grid, TileCfg::kThreads, smem, ctx->stream>>>(a);
   }
@@ -662,6 +681,8 @@ int configure_kernels(b200nav_ctx* ctx) {
   CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_kernel<kSub, kListCap>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
   CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_coded_kernel<kListCap>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_coded_mw_kernel<kListCap, kHeavyWarps>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
   CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
   CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));

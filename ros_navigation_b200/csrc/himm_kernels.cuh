@@ -84,6 +84,7 @@ struct HimmArgs {
   int n_chunks;                   /* chunks per robot                             */
   int chunk_beams;                /* beams per chunk: multiple of 32, <= HIMM_CHUNK */
   int mask_words;                 /* chunk_beams / 32                              */
+  int skip_heavy;                 /* the one-warp tile kernel leaves the heavy items to himm_tile_coded_mw_kernel */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -354,10 +355,16 @@ struct FloatView { /* global memory, in place (tiles with values outside the HIM
 
 /* Apply the listed beams, in order, to one tile through `view` (cell (r,c) of the tile lives at
  * view[(c-C0)*pitch + (r-R0)]).  32 list entries per batch; see the schedule description below. */
-template <class View>
+/* NW > 1: the NW warps of a CTA work on ONE tile together.  Every warp holds the same 32 beams of a batch; the
+ * rings of a fan batch are dealt round-robin in blocks of four steps (block = t >> 2, owner = block % NW).  A cell at
+ * step t of a line from origin O has Chebyshev distance t from O, so for batches that share their origin a cell
+ * always belongs to the same warp and that warp sees the batches in order: the per-cell order of the reference is
+ * kept with no barrier between batches.  A change of origin or a non-fan batch makes all warps meet first. */
+template <class View, int NW = 1>
 __device__ __forceinline__ void himm_apply_list(const View view, const int pitch, const BeamSeg* __restrict__ segs,
                                                 const uint16_t* list, const int n_list, const int R0, const int R1,
-                                                const int C0, const int C1, const int lane) {
+                                                const int C0, const int C1, const int lane, const int warp = 0) {
+  int cur_origin = -1; /* NW > 1: origin cell shared by the fan batches since the last block barrier */
   /* Lane-parallel set-up: lane L clips beam L of the batch to this tile and derives the Bresenham state at its
    * first step inside.  Then one of two exact schedules:
    *  (fan)     all beams of the batch start in the SAME cell (a lidar scan).  A cell at step t of such a line has
@@ -424,30 +431,28 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
        * them, so an iteration in which no lane sees a larger value and no lane marks needs no coordination at
        * all (the common case: free space).  Otherwise match.any groups the lanes by cell and the lowest lane of
        * each group applies the group's clears and +30 marks in lane order == sample order. ---- */
+      if (NW > 1) { /* batches of another origin may meet these cells at other steps: let every warp catch up */
+        const int origin = lr0 * 65536 + lc0;
+        if (cur_origin != origin) {
+          __syncthreads();
+          cur_origin = origin;
+        }
+      }
       const int first = (my_len > 0) ? my_t0 : 0x7fffffff;
       const unsigned span = (my_len > 0) ? (unsigned)(my_len - 1) : 0u;
       const int last = (my_len > 0) ? my_t0 + my_len - 1 : -0x7fffffff;
       const int tmin = __reduce_min_sync(0xffffffffu, first), tmax = __reduce_max_sync(0xffffffffu, last);
-      /* every lane starts at step tmin of ITS line (possibly before it enters the tile: such cells are never
-       * dereferenced) and then steps unconditionally: frac += S, the carry is the minor step */
-      const int back = (my_len > 0) ? my_t0 - tmin : 0;
-      const unsigned long long xs = dda_at(my_S, my_B, (unsigned)((my_len > 0) ? tmin : 0));
-      unsigned frac = (unsigned)xs;
-      const int qs = my_diag ? 0 : (int)(xs >> 32);
       const int step_plain = my_diag ? my_dm + my_dn : my_dm, step_carry = step_plain + my_dn;
-      int off = my_off0 - back * step_plain - (my_q0 - qs) * my_dn;
       const int mark_k = (my_moff >= 0) ? (int)span : -1; /* step (relative to `first`) that also marks */
-      int k = (my_len > 0) ? tmin - first : -0x40000000;
-      /* RINGS steps (disjoint rings of cells) per iteration.  Cells of different steps are different cells, so
-       * only the reads and writes of ONE iteration can meet: a single warp barrier between its read half and its
-       * write half orders them. */
+      /* RINGS steps (disjoint rings of cells) per block.  Cells of different steps are different cells, so only the
+       * reads and writes of ONE block can meet: a single warp barrier between its read half and its write half
+       * orders them.  Stepping is unconditional: frac += S, the carry is the minor step; cells before a line enters
+       * the tile or after it left are never dereferenced. */
       constexpr int RINGS = 4;
-      const int n_iter = (tmax - tmin) / RINGS;
-      const int mark_iter = (my_moff >= 0) ? (mark_k - k) / RINGS : -1; /* iteration in which this lane marks */
-      for (int i = 0; i <= n_iter; i++, k += RINGS) {
+      auto ring_block = [&](const int k, int& off, unsigned& frac) {
         int offs[RINGS];
         bool hot[RINGS]; /* my cell of ring r holds a value that counts visits (code >= 2) */
-        bool sens = (i == mark_iter);
+        bool sens = mark_k >= 0 && (unsigned)(mark_k - k) < (unsigned)RINGS; /* I mark inside this block */
 #pragma unroll
         for (int r = 0; r < RINGS; r++) {
           offs[r] = off;
@@ -458,7 +463,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           off += (nf < frac) ? step_carry : step_plain;
           frac = nf;
         }
-        __syncwarp(); /* all reads of this iteration are done before any lane writes (memory-model order) */
+        __syncwarp(); /* all reads of this block are done before any lane writes (memory-model order) */
         if (!__any_sync(0xffffffffu, sens)) {
 #pragma unroll
           for (int r = 0; r < RINGS; r++)
@@ -479,10 +484,39 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
             }
           }
         }
+      };
+      if (NW == 1) {
+        /* every lane starts at step tmin of ITS line and walks on from there */
+        const int back = (my_len > 0) ? my_t0 - tmin : 0;
+        const unsigned long long xs = dda_at(my_S, my_B, (unsigned)((my_len > 0) ? tmin : 0));
+        unsigned frac = (unsigned)xs;
+        const int qs = my_diag ? 0 : (int)(xs >> 32);
+        int off = my_off0 - back * step_plain - (my_q0 - qs) * my_dn;
+        int k = (my_len > 0) ? tmin - first : -0x40000000;
+        const int n_iter = (tmax - tmin) / RINGS;
+        for (int i = 0; i <= n_iter; i++, k += RINGS) ring_block(k, off, frac);
+      } else {
+        /* my blocks of four absolute steps: block b = t >> 2 belongs to warp b % NW; the state at the block's first
+         * step comes from the closed form */
+        const int blk_lo = tmin >> 2, blk_hi = tmax >> 2;
+        int blk = blk_lo + ((warp - blk_lo) % NW + NW) % NW;
+        for (; blk <= blk_hi; blk += NW) {
+          const int tb = blk << 2;
+          const unsigned long long xs = dda_at(my_S, my_B, (unsigned)tb);
+          unsigned frac = (unsigned)xs;
+          const int q = my_diag ? 0 : (int)(xs >> 32);
+          int off = my_off0 + (tb - my_t0) * step_plain + (q - my_q0) * my_dn;
+          ring_block((my_len > 0) ? tb - first : -0x40000000, off, frac);
+        }
       }
       __syncwarp(); /* the next batch may read any cell this one wrote */
     } else {
       /* ---- general schedule ---- */
+      if (NW > 1) { /* one warp applies the batch while the others wait: any cell may be involved */
+        __syncthreads();
+        cur_origin = -1;
+        if (warp != 0) active = 0u;
+      }
       while (active) {
         const int src = __ffs(active) - 1;
         active &= active - 1;
@@ -521,6 +555,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           __syncwarp();
         }
       }
+      if (NW > 1) __syncthreads();
     }
   }
 }
@@ -844,7 +879,8 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
   const int rows = a.dims.rows, cols = a.dims.cols;
   const int n_tiles = a.tiles_r * a.tiles_c;
   const int n_heavy = *reinterpret_cast<volatile int*>(&a.counters[0]); /* final: the prep kernel has completed */
-  const int n_work = n_heavy + *reinterpret_cast<volatile int*>(&a.counters[3]);
+  const int n_light = *reinterpret_cast<volatile int*>(&a.counters[3]);
+  const int n_work = a.skip_heavy ? n_light : n_heavy + n_light;
   if (lane == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -857,7 +893,8 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
     if (lane == 0) w = atomicAdd(&a.counters[1], 1);
     w = __shfl_sync(0xffffffffu, w, 0);
     if (w >= n_work) break;
-    const int rt = a.worklist[w < n_heavy ? w : a.worklist_cap - 1 - (w - n_heavy)];
+    const int rt = a.skip_heavy ? a.worklist[a.worklist_cap - 1 - w]
+                                : a.worklist[w < n_heavy ? w : a.worklist_cap - 1 - (w - n_heavy)];
     const int rel = rt / n_tiles, tile_id = rt - rel * n_tiles;
     const int robot = a.robot0 + rel;
     const int tile_r = tile_id % a.tiles_r, tile_c = tile_id / a.tiles_r;
@@ -974,6 +1011,118 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
       a.counters[3] = 0;
     }
   }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K1 for the "heavy" work items (the tile that holds a scan's own origin sees every beam of it) when there are few
+ * robots: NW warps share one tile (see himm_apply_list<View, NW>), which cuts the latency of the longest item of a
+ * single-robot update.  CTA b handles heavy items b, b + gridDim.x, ...; the one-warp kernel then only takes the
+ * light items (HimmArgs::skip_heavy).
+ * ------------------------------------------------------------------------------------------------------------- */
+template <int LIST_CAP, int NW>
+__global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a) {
+  static_assert(LIST_CAP == HIMM_CHUNK, "chunk constant");
+  extern __shared__ __align__(128) unsigned char himm_smem_raw[];
+  uint8_t* tile = himm_smem_raw;
+  uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + HIMM_TILE_BYTES);
+  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ int s_nlist;
+
+  uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
+  asm volatile("mov.u32 %0, %0;" : "+r"(tile_saddr));
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows = a.dims.rows, cols = a.dims.cols;
+  const int n_tiles = a.tiles_r * a.tiles_c;
+  const int n_heavy = *reinterpret_cast<volatile int*>(&a.counters[0]);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+
+  for (int item = blockIdx.x; item < n_heavy; item += gridDim.x) {
+    const int rt = a.worklist[item];
+    const int rel = rt / n_tiles, tile_id = rt - rel * n_tiles;
+    const int robot = a.robot0 + rel;
+    const int tile_r = tile_id % a.tiles_r, tile_c = tile_id / a.tiles_r;
+    const int R0 = tile_r * HIMM_TILE, C0 = tile_c * HIMM_TILE;
+    const int R1 = min(R0 + HIMM_TILE, rows) - 1, C1 = min(C0 + HIMM_TILE, cols) - 1;
+    int beg;
+    if (a.single_n >= 0) beg = 0;
+    else beg = __ldg(&a.offsets[rel]);
+    uint8_t* grec = static_cast<uint8_t*>(a.layer) + ((size_t)robot * n_tiles + tile_id) * HIMM_TILE_BYTES;
+    const bool known_free = a.free_cols[rt] == ~0ull;
+    if (threadIdx.x == 0) {
+      a.touched[rt] = 0u;
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* the previous item's store has read the buffer */
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "n"(HIMM_TILE_BYTES) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(tile_saddr), "l"(grec), "n"(HIMM_TILE_BYTES), "r"(mbar)
+                   : "memory");
+    }
+    bool ready = false;
+
+    for (int chunk = 0; chunk < a.n_chunks; chunk++) {
+      if (warp == 0) { /* mask -> ordered beam list, as in the one-warp kernel */
+        const size_t t = ((size_t)rel * a.n_chunks + chunk) * (size_t)n_tiles + tile_id;
+        uint32_t* mw = a.beam_masks + t * a.mask_words;
+        const uint32_t w0 = (lane < a.mask_words) ? mw[lane] : 0u, w1 = (lane + 32 < a.mask_words) ? mw[lane + 32] : 0u;
+        if (w0) mw[lane] = 0u;
+        if (w1) mw[lane + 32] = 0u;
+        const int p0 = __popc(w0), p1 = __popc(w1);
+        int inc0 = p0, inc1 = p1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u0 = __shfl_up_sync(0xffffffffu, inc0, o), u1 = __shfl_up_sync(0xffffffffu, inc1, o);
+          if (lane >= o) {
+            inc0 += u0;
+            inc1 += u1;
+          }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+        const int n = tot0 + __shfl_sync(0xffffffffu, inc1, 31);
+        int pos = inc0 - p0;
+        for (uint32_t ww = w0; ww; ww &= ww - 1) list[pos++] = (uint16_t)(32 * lane + __ffs(ww) - 1);
+        pos = tot0 + inc1 - p1;
+        for (uint32_t ww = w1; ww; ww &= ww - 1) list[pos++] = (uint16_t)(32 * (lane + 32) + __ffs(ww) - 1);
+        if (lane == 0) s_nlist = n;
+      }
+      __syncthreads();
+      const int n_list = s_nlist;
+      if (n_list > 0) {
+        if (!ready) {
+          mbar_wait(mbar, phase);
+          phase ^= 1u;
+          ready = true;
+        }
+        if (threadIdx.x == 0) atomicAdd(&a.counters[5], 1); /* statistics: tiles processed */
+        const BeamSeg* segs = a.segs + beg + chunk * a.chunk_beams;
+        himm_apply_list<CodeView, NW>(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane, warp);
+      }
+      __syncthreads(); /* all warps are done with the list (and with the tile, after the last chunk) */
+    }
+    if (!ready) {
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+    }
+    unsigned diff = 0;
+    for (int i = threadIdx.x; i < HIMM_TILE_BYTES / 16; i += blockDim.x) {
+      uint32_t x, y, z, q;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(q) : "r"(tile_saddr + 16 * i) : "memory");
+      diff |= (x ^ 0x01010101u) | (y ^ 0x01010101u) | (z ^ 0x01010101u) | (q ^ 0x01010101u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const bool all_free = __syncthreads_or(diff != 0u) == 0;
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grec), "r"(tile_saddr), "n"(HIMM_TILE_BYTES) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (all_free != known_free) a.free_cols[rt] = all_free ? ~0ull : 0ull;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace b200nav

@@ -129,3 +129,13 @@ def test_float_layer_mode_runs_the_same_suites():
                           "-x", "-q", "-k", "not very_long and not full_size", "-p", "no:cacheprovider"],
                          cwd=ROOT, env=env, capture_output=True, text=True, timeout=400)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_multi_warp_heavy_tile_kernel_runs_the_himm_suite():
+    """B200NAV_MW_HEAVY=1 hands the tile that holds a scan's origin to a CTA of four warps that split the rings of
+    the tile among them (himm_tile_coded_mw_kernel, experimental): same bits as the one-warp kernel."""
+    env = dict(os.environ, B200NAV_MW_HEAVY="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_himm_gpu.py", "-m", "gpu", "-x", "-q", "-k",
+                          "random or order or chunking or several or edge or batched or cloud_form_matches or long_steady",
+                          "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=400)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
