@@ -485,6 +485,7 @@ int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, c
 int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int rel_lo, int rel_hi) {
   b200nav_ctx* ctx = g->ctx;
   if (beam_hi <= beam_lo) return B200NAV_OK;
+  ctx->prep_done_valid = false; /* a new reader of the staging buffers: the asynchronous paths re-arm it after the launch */
   a.beam_lo = beam_lo;
   a.beam_hi = beam_hi;
   a.rel_lo = rel_lo;
