@@ -243,12 +243,18 @@ class VFH {
   int Update_VFH_FromGrid(GridLayers& map, const std::string& layer, double x, double y, double yaw, int current_speed,
                           float goal_direction, float goal_distance, float goal_distance_tolerance, int& chosen_speed,
                           int& chosen_turnrate) {
+    return update_from_device_grid(map.get(), layer, x, y, yaw, current_speed, goal_direction, goal_distance,
+                                   goal_distance_tolerance, chosen_speed, chosen_turnrate);
+  }
+  int update_from_device_grid(b200nav_grid* grid, const std::string& layer, double x, double y, double yaw,
+                              int current_speed, float goal_direction, float goal_distance,
+                              float goal_distance_tolerance, int& chosen_speed, int& chosen_turnrate) {
     b200nav_vfh_input in = make_input(current_speed, goal_direction, goal_distance, goal_distance_tolerance);
     in.x = x;
     in.y = y;
     in.yaw = yaw;
     b200nav_command out;
-    if (vfh_ && b200nav_vfh_update_grid(vfh_, map.get(), layer.c_str(), 0, &in, &out) == B200NAV_OK)
+    if (vfh_ && b200nav_vfh_update_grid(vfh_, grid, layer.c_str(), 0, &in, &out) == B200NAV_OK)
       finish(out, chosen_speed, chosen_turnrate);
     return 1;
   }

@@ -570,11 +570,13 @@ int oracle_if_blocked(const oracle_geom* g, const float* master, double x, doubl
 
 void oracle_goal_from_pose(double rx, double ry, double yaw, double tx, double ty, float* desired_angle,
                            float* desired_dist) {
-  /* steerer.cpp:228-256: float deltaX/deltaY/desiredDist; hypot on floats; RAD2DEG(normalize_angle_positive()) */
+  /* steerer.cpp:228-256: float deltaX/deltaY/desiredDist; RAD2DEG(normalize_angle_positive()).  steerer.cpp includes
+   * <math.h>, whose C++ form exposes the float overloads: hypot(float, float) and atan2(float, float) are hypotf and
+   * atan2f there (checked against the reference's own Steerer::update, tests/test_reference_pin.py). */
   const float dX = static_cast<float>((tx - rx) * 1000.0);
   const float dY = static_cast<float>((ty - ry) * 1000.0);
-  *desired_dist = hypot(dX, dY);
-  const double a = atan2(dY, dX) - yaw + M_PI / 2;
+  *desired_dist = std::hypot(dX, dY);
+  const double a = std::atan2(dY, dX) - yaw + M_PI / 2;
   const double np = fmod(fmod(a, 2.0 * M_PI) + 2.0 * M_PI, 2.0 * M_PI);
   *desired_angle = static_cast<float>(np * 180.0 / M_PI);
 }
@@ -636,7 +638,8 @@ int oracle_scan_select(float angle_increment, int n_ranges, int decimate, int* s
 }
 
 int oracle_project_scan(float angle_min, float increment_used, float range_min, float range_max, const int* sel,
-                        int n_used, const float* ranges, double x0, double y0, double yaw, oracle_sample* out) {
+                        int n_used, int decimated, const float* ranges, double x0, double y0, double yaw,
+                        oracle_sample* out) {
   double sin_yaw, cos_yaw;
   oracle_sincos(yaw, &sin_yaw, &cos_yaw);
   int n = 0;
@@ -656,7 +659,10 @@ int oracle_project_scan(float angle_min, float increment_used, float range_min, 
     out[n].sy = y0;
     out[n].ex = map_x; /* Position(*itX, *itY) */
     out[n].ey = map_y;
-    out[n].clear_end = 0;
+    /* laser_map_updater.cpp:62-66: `index` is the point's position in the projected (possibly thinned) scan, but it is
+     * looked up in the ORIGINAL msg->ranges.  Not thinned: that reading passed the filter above, flag false. */
+    const float looked_up = decimated ? ranges[j] : range;
+    out[n].clear_end = (std::isinf(looked_up) || looked_up == range_max) ? 1 : 0;
     out[n].pad_ = 0;
     n++;
   }

@@ -72,7 +72,7 @@ def lib():
         L.oracle_compose_master.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
         L.oracle_sincos.argtypes = [C.c_double, _dp, _dp]
         L.oracle_scan_select.argtypes = [C.c_float, C.c_int, C.c_int, C.c_void_p, _fp]
-        L.oracle_project_scan.argtypes = [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p] + [C.c_double] * 3 + [C.c_void_p]
+        L.oracle_project_scan.argtypes = [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_double] * 3 + [C.c_void_p]
         _lib = L
     return _lib
 
@@ -229,7 +229,8 @@ def project_scan(angle_min, angle_increment, range_min, range_max, ranges, pose,
     sel, used = scan_select(np.float32(angle_increment), len(ranges), decimate)
     out = np.zeros(len(sel), dtype=SAMPLE_DTYPE)
     n = lib().oracle_project_scan(float(np.float32(angle_min)), used, float(np.float32(range_min)),
-                                  float(np.float32(range_max)), sel.ctypes.data, len(sel), ranges.ctypes.data,
+                                  float(np.float32(range_max)), sel.ctypes.data, len(sel),
+                                  int(bool(decimate) and float(np.float32(angle_increment)) < 0.017), ranges.ctypes.data,
                                   float(pose[0]), float(pose[1]), float(pose[2]), out.ctypes.data)
     return out[:n].copy()
 

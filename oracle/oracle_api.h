@@ -105,7 +105,8 @@ void oracle_sincos(double x, double* s, double* c);
 int oracle_scan_select(float angle_increment, int n_ranges, int decimate, int* sel, float* increment_used);
 /* Samples of one scan taken at sensor pose (x0, y0, yaw); dropped readings are skipped.  Returns the sample count. */
 int oracle_project_scan(float angle_min, float increment_used, float range_min, float range_max, const int* sel,
-                        int n_used, const float* ranges, double x0, double y0, double yaw, oracle_sample* out);
+                        int n_used, int decimated, const float* ranges, double x0, double y0, double yaw,
+                        oracle_sample* out);
 
 #ifdef __cplusplus
 }

@@ -1756,6 +1756,7 @@ static int himm_update_scans(b200nav_grid* g, const char* layer, const b200nav_s
   c.scan.range_max = info->range_max;
   c.scan.n_ranges = info->n_ranges;
   c.scan.n_used = n_used;
+  c.scan.decimated = (info->decimate && info->angle_increment < 0.017f) ? 1 : 0;
   HimmArgs a;
   int rc = himm_setup(g, l, nullptr, static_cast<const int32_t*>(g->scan_offsets.p), 0, nr, -1, nr * n_used, n_used, c, a);
   if (rc) return rc;

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
       const int j = i - beg;
       const int src = a.scan_sel ? __ldg(&a.scan_sel[j]) : j;
       const float r = __ldg(&a.scan_ranges[(size_t)rel * a.scan.n_ranges + src]);
-      clear_end = 0;
+      clear_end = (a.scan.decimated && scan_clear_end(a.scan, __ldg(&a.scan_ranges[(size_t)rel * a.scan.n_ranges + j]))) ? 1 : 0;
       if (!project_reading(a.scan, j, r, sx, sy, cyaw, syaw, ex, ey)) ex = ey = __longlong_as_double(0x7ff8000000000000ll);
     } else { /* cloud form: Position(*itX, *itY) widens the float32 cloud point (laser_map_updater.cpp:60) */
       const float2 p = a.xy[i];

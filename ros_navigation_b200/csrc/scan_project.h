@@ -17,8 +17,12 @@
  *   map frame   sensor pose (x0, y0, yaw) in the map frame at the scan's stamp (one transform per scan: the per-point
  *               time interpolation of the high-fidelity projection is not modelled):
  *               X = (float)((cos(yaw) * (double)lx - sin(yaw) * (double)ly) + x0), Y likewise with (sin, cos) and y0.
- *   sample      start = (x0, y0) (getLaserOriginOnGlobal), end = ((double)X, (double)Y), ifClearEnd = false (readings
- *               at or beyond range_max never reach the loop, laser_map_updater.cpp:62-66).
+ *   sample      start = (x0, y0) (getLaserOriginOnGlobal), end = ((double)X, (double)Y).  ifClearEnd
+ *               (laser_map_updater.cpp:62-66) is read from msg->ranges[index] with `index` the point's position in the
+ *               PROJECTED scan but `msg` the ORIGINAL one: for a scan that was not thinned that reading passed the
+ *               range filter, so the flag is false; for a thinned scan the j-th selected reading gets
+ *               ifClearEnd = isinf(ranges[j]) || ranges[j] == range_max of the original scan (a reference quirk, kept:
+ *               verified against the reference's own bufferIncomingMsg, tests/test_reference_pin.py).
  *   sin / cos   b200nav_sincos below: a fixed sequence of individually rounded fp64 operations (Cody-Waite reduction
  *               by pi/2 in three 33-bit pieces, the classic degree-13 / degree-14 minimax kernels), so that a CPU
  *               restatement and the GPU produce the same bits.  |x| < 2^20 * pi/2; about 1 ulp.
@@ -64,7 +68,14 @@ struct ScanModel {
   float range_min, range_max;
   int n_ranges;         /* ranges per robot in the input array                */
   int n_used;           /* selected ranges per robot (== samples per robot)   */
+  int decimated;        /* simplifyLaserScan thinned the scan (angle_increment < 0.017) */
 };
+
+/* ifClearEnd of the j-th projected point: laser_map_updater.cpp:62-66 indexes the ORIGINAL scan with j. */
+B200_HD bool scan_clear_end(const ScanModel& m, float original_range_at_j) {
+  return m.decimated && (original_range_at_j == m.range_max || original_range_at_j == INFINITY ||
+                         original_range_at_j == -INFINITY);
+}
 
 /* j-th selected range of one scan -> sample end point; returns false when the reading is dropped. */
 B200_HD bool project_reading(const ScanModel& m, int j, float r, double x0, double y0, double cy, double sy,
