@@ -147,42 +147,62 @@ class ClockSampler:
 # CPU arm: the reference's CPU algorithm on the host cores (oracle restatement + reference vfh.cpp)
 # ----------------------------------------------------------------------------------------------------------------
 class CpuArm:
-    """HIMM + pseudo-scan restatement (oracle/himm_oracle.cpp) and the reference VFH class (oracle/_ref) for a
-    bounded sample of robots, one Python thread per host core (the C calls release the GIL)."""
+    """The reference's CPU implementation of the path on the host cores, for a bounded sample of robots.
+
+    kind "reference" (configs whose geometry the reference's MapProvider / Steerer hard-code: 5 cm cells, 30-cell VFH
+    window, 1.5 m submap = c1, c2, c4, c5): oracle/_ref/libnav_ref.so = the reference's own move_control and
+    grid_map_core sources compiled in place.  Every robot is one reference node (MapProvider + LaserMapUpdater +
+    Steerer + VFH); a cycle is ONE native call (navh_fleet_cycle_samples) that block-partitions the robots over
+    std::threads - no Python in the loop: the scan's RangeSamples go into the LaserMapUpdater's buffer, then
+    MapProvider::updateMap (per-cell string-keyed layer lookup, master := laser copy) and Steerer::update (submap copy
+    of all layers, pseudo-scan, VFH::Update_VFH) run as written.
+    kind "port" (c3: 2 cm cells / 129-cell window cannot be configured in the reference's node classes, or when
+    oracle/_ref is missing): oracle restatement of HIMM + pseudo-scan and the reference vfh.cpp, one robot per core."""
 
     def __init__(self, cfg_name, n_robots, n_cycles=4):
         import numpy as np
         import torch
+        from oracle import navref as N
         from oracle import oracle as O
         from ros_navigation_b200 import synth
-        self.O, self.np = O, np
-        self.cores = max(1, min(os.cpu_count() or 1, n_robots))
+        self.O, self.N, self.np = O, N, np
         self.n = n_robots
         cyc = Cycles(cfg_name, 0, n_robots, torch.device("cpu"), n_cycles=n_cycles, want_samples=True)
         self.cfg = cfg = cyc.cfg
-        self.geom = O.make_geom(cfg["extent"], cfg["extent"], cfg["res"])
-        self.layers = [O.new_layer(self.geom) for _ in range(n_robots)]
-        # HIMM / pseudo-scan: the oracle's restatement (the reference's grid_map / ROS side does not build here);
-        # VFH+: the unmodified reference vfh.cpp when oracle/_ref is present.  Reported as "port" (the weaker claim).
-        self.kind = "port"
-        self.parts = ("HIMM + pseudo-scan: oracle restatement; VFH+: " +
-                      ("unmodified reference vfh.cpp" if O.have_ref() else "not run (oracle/_ref missing)"))
-        self.vfh = None
-        if O.have_ref():
-            self.vfh = [O.RefVFH(window_diameter=cfg["window"], cell_size=cfg["cell"]) for _ in range(n_robots)]
+        self.cores = max(1, min(os.cpu_count() or 1, n_robots))
         self.samples = [synth.samples_to_numpy(s) for s in cyc.samples]
         self.offsets = [o.numpy() for o in cyc.offsets]
         self.inputs = [synth.vfh_inputs_to_numpy(i) for i in cyc.inputs]
         self.n_cycles = n_cycles
         self.submap = cfg["submap"]
+        node_shaped = (cfg["res"] == 0.05 and cfg["window"] == 30 and cfg["cell"] == 100.0 and cfg["submap"] == 1.5)
+        self.cycle_no = 0
+        if N.have_ref() and node_shaped and not os.environ.get("B200NAV_CPU_PORT"):
+            self.kind = "reference"
+            self.parts = ("reference move_control + grid_map_core sources compiled in place (oracle/_ref/libnav_ref.so): "
+                          "MapProvider::updateMap + Steerer::update per robot, std::thread pool inside one native call")
+            self.nodes = [N.Node(N.REF_PATH, cfg["extent"], cfg["extent"], False, t0=1.0) for _ in range(n_robots)]
+            self.poses = [np.stack([i["x"], i["y"], i["yaw"]], 1) for i in self.inputs]
+            self.speeds = [i["current_speed"].astype(np.float64) / 1000.0 for i in self.inputs]
+            self.goals = []
+            for c in range(n_cycles):   # the waypoint behind synth.vfh_inputs' goal_direction / goal_distance
+                gx, gy, _ = cyc.worlds.pose(c * cyc.dt * 5 + 15.0)
+                self.goals.append(np.stack([gx.numpy(), gy.numpy()], 1))
+            return
+        self.kind = "port"
+        self.parts = ("HIMM + pseudo-scan: oracle restatement; VFH+: " +
+                      ("unmodified reference vfh.cpp" if O.have_ref() else "not run (oracle/_ref missing)"))
+        self.geom = O.make_geom(cfg["extent"], cfg["extent"], cfg["res"])
+        self.layers = [O.new_layer(self.geom) for _ in range(n_robots)]
+        self.vfh = None
+        if O.have_ref():
+            self.vfh = [O.RefVFH(window_diameter=cfg["window"], cell_size=cfg["cell"]) for _ in range(n_robots)]
 
     def _robot_cycle(self, r, c):
         O = self.O
         off = self.offsets[c]
         O.himm_update(self.geom, self.layers[r], self.samples[c][off[r]:off[r + 1]])
         inp = self.inputs[c][r]
-        # master := laser is aliased on the GPU side; the reference copies the layer (map_provider.cpp:221) - the
-        # copy is excluded on both sides (SURVEY section 8d).
         rng = O.ranges_from_submap(self.geom, self.layers[r], float(inp["x"]), float(inp["y"]), float(inp["yaw"]),
                                    self.submap)
         if self.vfh is not None:
@@ -192,6 +212,13 @@ class CpuArm:
     def run_cycle(self, c):
         """One cycle over all sample robots on all cores; returns seconds."""
         c = c % self.n_cycles
+        if self.kind == "reference":
+            self.cycle_no += 1
+            t0 = time.perf_counter()
+            self.last_cmd = self.N.fleet_cycle_samples(self.nodes, 1.0 + 0.2 * self.cycle_no, self.poses[c],
+                                                       self.samples[c], self.offsets[c], self.goals[c], self.speeds[c],
+                                                       threads=self.cores)
+            return time.perf_counter() - t0
         chunks = [list(range(i, self.n, self.cores)) for i in range(self.cores)]
 
         def work(rs):
@@ -209,8 +236,10 @@ class CpuArm:
 
 def cpu_sample_size(cfg_name):
     """Robots in the CPU arm's bounded sample.  Single-robot configurations (c1-c3) are one robot on ONE core, as the
-    reference runs them; batched configurations use a robot sample spread over all host cores."""
-    return {"c1": 1, "c2": 1, "c3": 1, "c4": 256, "c5": 512}.get(cfg_name, 64)
+    reference runs them; batched configurations use a robot sample spread over all host cores (at least 8 robots per
+    core so that the block partition is balanced)."""
+    cores = os.cpu_count() or 1
+    return {"c1": 1, "c2": 1, "c3": 1, "c4": max(256, 8 * cores), "c5": max(512, 16 * cores)}.get(cfg_name, 64)
 
 
 def run_reference_arm(args, rank, world):
@@ -368,6 +397,14 @@ class GpuArm:
         h2d = self.h_poses[c].numel() * 8 + self.h_ranges[c].numel() * 4 + self.h_inputs[c].numel()
         return h2d, self.h_cmd.numel()
 
+    def tile_stats(self):
+        """(tile work items dropped by the known-free shortcut, items walked) since the previous call."""
+        import numpy as np
+        from ros_navigation_b200.capi import lib
+        out = np.zeros(2, np.int64)
+        lib().b200nav_himm_debug_tile_stats(self.grid.h, out.ctypes.data)
+        return int(out[0]), int(out[1])
+
     def algorithmic_bytes(self, c):
         """8 B per cell visit + 8 B per mark + 36 B per beam, for cycle c (this rank)."""
         self.step_himm_only(c)
@@ -442,6 +479,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
         arm.ctx.profile_enable(True)
         launches0 = arm.ctx.launches
+        arm.tile_stats()   # reset the skipped / processed counters
         t_wall0 = time.perf_counter()
         ms = timed_steps(torch, stream, arm.step_dev, args.warmup, args.steps, arm)
         torch.cuda.synchronize()
@@ -449,10 +487,18 @@ def run_gpu_arm(args, rank, world, local_rank):
             dist.barrier()
         wall = time.perf_counter() - t_wall0
         launches = arm.ctx.launches - launches0
+        tiles_skipped, tiles_processed = arm.tile_stats()
         tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
         prep_ms, prep_n = arm.ctx.profile_read("himm_prep")
         vfh_ms, vfh_n = arm.ctx.profile_read("vfh_update")
         arm.ctx.profile_enable(False)
+        # ---- outside the timed region: proof that the exchange delivered every rank's rows to every rank ----
+        exchange_bad = None
+        if arm.exchange is not None:
+            exchange_bad = 0
+            for k in range(2):   # one more cycle per slot, then checksum every rank's block on every rank
+                arm.step_dev(args.warmup + args.steps + k, last=True)
+                exchange_bad += arm.exchange.verify((args.warmup + args.steps + k) & 1)
         # ---- end-to-end: host buffers through the C ABI ----
         arm.run_e2e_pipelined(0, max(3, args.warmup // 2))
         # cost of the in-stream L2 flushes alone (reported next to the raw number, never subtracted from it)
@@ -470,6 +516,23 @@ def run_gpu_arm(args, rank, world, local_rank):
         e2e_s = time.perf_counter() - t0
         clk = clocks.stop() if rank == 0 else None
 
+    # first-pass number (all ranks take part): layers cleared to NaN, the first N_CYCLES cycles timed
+    cold = None
+    if not args.no_extra:
+        try:
+            cold = cold_grid_numbers(torch, stream, arm, robots_total, alg, hbm_peak)
+        except Exception as e:
+            cold = {"error": repr(e)}
+    # N > 1: the same run also shards the configurations' FIXED robot counts over the ranks (strong scaling):
+    # BASELINE config 4 (1024 robots / N per GPU) and config 5 (16 384 robots / N per GPU, with the all-gather)
+    sharded = None
+    if world > 1 and not args.no_extra and args.scaling == "weak":
+        sharded = {}
+        for name in ("c4", "c5"):
+            try:
+                sharded[name] = sharded_numbers(torch, dist, device, name, rank, world)
+            except Exception as e:
+                sharded[name] = {"error": repr(e)}
     total_ms = float(sum(ms))
     t = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=device)
     if world > 1:
@@ -508,16 +571,42 @@ def run_gpu_arm(args, rank, world, local_rank):
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "avg_launch_ms": tile_avg_ms, "launches_timed": int(tile_n),
-                     "visits_per_launch": float(np.mean([u[1] for u in used]))},
+                     "visits_per_launch": float(np.mean([u[1] for u in used])),
+                     "tile_items_per_launch": {"walked": tiles_processed / max(args.steps, 1),
+                                               "dropped_known_free": tiles_skipped / max(args.steps, 1),
+                                               "note": "steady state (free space already 0): a touched tile whose cells are "
+                                                       "all 0 and that receives no mark cannot change and is dropped before any "
+                                                       "copy; its visits are still counted in algorithmic_bytes (the reference "
+                                                       "performs them) - see cold_grid for the first-pass number"}},
         "kernel_ms_per_step": {"himm_prep": prep_ms / max(prep_n, 1), "himm_tile": tile_avg_ms,
                                "vfh_update": vfh_ms / max(vfh_n, 1)},
         "wall_s_timed_region": wall,
         "host_enqueue_ms_per_step": getattr(arm, "host_enqueue_ms_per_step", None),
+        "exchange_verified": (None if exchange_bad is None else
+                              {"ranks": world, "mismatching_blocks": exchange_bad,
+                               "how": "after the timed region: 2 more cycles, every rank checksums each rank's block of "
+                                      "the table it received against the producer's own checksum (all-gathered)"}),
         "exchange": (None if arm.exchange is None else
                      ("peer push fused into the VFH+ kernel (NVLink P2P stores)" if arm.exchange.push else
                       ("NCCL all-gather, library binding" if arm.exchange.fleet is not None else
                        "torch.distributed all-gather"))),
     }
+    # The resource that actually binds the tile kernel is warp-instruction issue (ncu: DRAM ~12 %, issue ~70 %): second
+    # roofline = warp instructions per launch (ncu smsp__inst_executed.sum of the same workload, profiles/issue.json)
+    # / this run's launch time, against 148 SMs x 4 schedulers x 1 instruction per clock at the sampled SM clock.
+    try:
+        issue = json.load(open(os.path.join(ROOT, "profiles", "issue.json"))).get(args.workload)
+    except Exception:
+        issue = None
+    if issue and clk and clk.get("sm_mhz"):
+        peak_issue = 148 * 4 * clk["sm_mhz"] * 1e6
+        ach = issue["warp_instructions_per_launch"] / (tile_avg_ms / 1e3)
+        line["roofline_issue"] = {"bound": "issue", "kernel": "himm_tile_coded_kernel", "achieved": ach / 1e9,
+                                  "peak": peak_issue / 1e9, "unit": "G warp-instructions/s", "frac": ach / peak_issue,
+                                  "warp_instructions_per_launch": issue["warp_instructions_per_launch"],
+                                  "warp_instructions_per_visit": issue["warp_instructions_per_launch"] /
+                                  max(float(np.mean([u[1] for u in used])), 1.0),
+                                  "source": issue.get("source")}
     # the two smaller kernels against the same HBM peak (SURVEY section 8d accounting; both are latency bound)
     beams = float(np.mean([u[3] for u in used]))
     n_sub = int(math.ceil(arm.cfg["submap"] / arm.cfg["res"])) + 1
@@ -544,9 +633,16 @@ def run_gpu_arm(args, rank, world, local_rank):
                                         cpu.n, n_cyc, args.workload, secs)}
         except Exception as e:  # the baseline must never take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
+    if cold is not None:
+        line["cold_grid"] = cold
+    if sharded is not None:
+        line["strong_scaling"] = sharded
     if world == 1 and args.workload == "c4" and not args.no_extra:
+        del arm
+        torch.cuda.empty_cache()
         line["other_workloads"] = {}
-        for key, fn in (("c2", single_robot_numbers), ("c5", batched_numbers)):
+        for key, fn in (("c1", single_robot_numbers), ("c2", single_robot_numbers), ("c3", single_robot_numbers),
+                        ("c5", batched_numbers), ("c4_float_layers", float_layer_numbers)):
             try:
                 line["other_workloads"][key] = fn(device, key)
             except Exception as e:
@@ -554,8 +650,81 @@ def run_gpu_arm(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def cold_grid_numbers(torch, stream, arm, robots_total, alg, hbm_peak):
+    """The same workload on a map that knows nothing yet: every layer cleared to NaN, then the first N_CYCLES cycles
+    (nothing is known free, every touched tile is walked, every end cell is marked for the first time)."""
+    import numpy as np
+    with torch.cuda.stream(stream):
+        if arm.exchange is not None:
+            arm.exchange.wait()
+        arm.grid.clear("laser")
+        stream.synchronize()
+        arm.ctx.profile_enable(True)
+        arm.tile_stats()
+        ms = timed_steps(torch, stream, arm.step_dev, 0, N_CYCLES, arm)
+        skipped, walked = arm.tile_stats()
+        tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
+        arm.ctx.profile_enable(False)
+    t = torch.tensor([float(sum(ms))], dtype=torch.float64, device=arm.cyc.device)
+    if arm.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    alg_bytes = float(np.mean([a[0] for a in alg]))
+    tile_avg = tile_ms / max(tile_n, 1)
+    return {"value": robots_total * N_CYCLES / (total_ms / 1000.0), "unit": UNIT, "ms_per_step": total_ms / N_CYCLES,
+            "steps": N_CYCLES, "himm_tile_ms": tile_avg,
+            "roofline_frac": alg_bytes / (tile_avg / 1e3) / 1e9 / hbm_peak,
+            "tile_items_per_launch": {"walked": walked / N_CYCLES, "dropped_known_free": skipped / N_CYCLES},
+            "how": "layer cleared to NaN, cycles 0..%d timed with CUDA events, L2 flushed before each" % (N_CYCLES - 1)}
+
+
+def sharded_numbers(torch, dist, device, name, rank, world, steps=12, warm=40):
+    """A configuration's own robot count split over the ranks (every rank calls this): device-timed like the main
+    line (events per step, L2 flushed, barrier on both sides, max over ranks), exchange included and verified."""
+    from ros_navigation_b200 import synth
+    robots_total = synth.CONFIGS[name]["robots"]
+    lo, hi = local_robot_range(robots_total, rank, world)
+    stream = torch.cuda.Stream(device)
+    with torch.cuda.stream(stream):
+        arm = GpuArm(name, lo, hi, device, stream, world, robots_total)
+        for w in range(warm):
+            arm.step_dev(w, last=True)
+        stream.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = timed_steps(torch, stream, arm.step_dev, warm, steps, arm)
+        torch.cuda.synchronize()
+        dist.barrier()
+        bad = 0
+        if arm.exchange is not None:
+            for k in range(2):
+                arm.step_dev(warm + steps + k, last=True)
+                bad += arm.exchange.verify((warm + steps + k) & 1)
+    t = torch.tensor([float(sum(ms))], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"workload": workload_config(name, world, robots_total)["workload"], "robots_per_gpu": hi - lo,
+           "value": robots_total * steps / (float(t[0]) / 1000.0), "unit": UNIT, "ms_per_step": float(t[0]) / steps,
+           "scaling": "strong", "exchange_mismatching_blocks": bad}
+    if arm.exchange is not None:
+        arm.exchange.close()
+    del arm
+    torch.cuda.empty_cache()
+    return out
+
+
+def float_layer_numbers(device, name, steps=12):
+    """C4 on FLOAT layers (the reference's own column-major float matrices in HBM) instead of the byte-coded tile
+    records: what the path costs when the layer layout north_star names is kept on the device."""
+    out = batched_numbers(device, "c4", steps=steps, warm=60, float_layers=True)
+    out["layers"] = "float [robot][col][row] (Eigen::MatrixXf layout), 4 B per cell"
+    out["roofline"]["kernel"] = "himm_tile_kernel (FloatView)"
+    return out
+
+
 def single_robot_numbers(device, name, scans=300):
-    """BASELINE config 2: one robot, 2048x2048 grid, 1080-beam scans replayed back to back (latency bound)."""
+    """The single-robot configurations (C1 200x200 / 360 beams, C2 2048x2048 / 1080 beams, C3 8192x8192 @ 2 cm /
+    4096 beams / 129-cell VFH window): scans replayed back to back (latency bound: one robot cannot fill the GPU)."""
     import torch
     stream = torch.cuda.Stream(device)
     with torch.cuda.stream(stream):
@@ -584,10 +753,10 @@ def single_robot_numbers(device, name, scans=300):
     arm.ctx.profile_enable(False)
     return {"workload": workload_config(name, 1, 1)["workload"], "value": scans / (dev_ms / 1000.0),
             "e2e": scans / e2e_s, "unit": UNIT, "ms_per_scan": dev_ms / scans, "kernel_ms": kms,
-            "l2": "grid (4.3 MiB of byte-coded tile records) L2-resident"}
+            "l2": "no flush: consecutive scans of one robot hit the same tile records"}
 
 
-def batched_numbers(device, name, steps=12):
+def batched_numbers(device, name, steps=12, warm=12, float_layers=False):
     """A second batched configuration (BASELINE config 5: 16384 robots x 256x256) on this GPU: device-resident value
     and the tile kernel's roofline fraction, measured like the main line (events per step, L2 flushed)."""
     import numpy as np
@@ -597,23 +766,31 @@ def batched_numbers(device, name, steps=12):
     robots = synth.CONFIGS[name]["robots"]
     with torch.cuda.stream(stream):
         arm = GpuArm(name, 0, robots, device, stream, 1)
+        if float_layers:   # asking for the raw device pointer moves the layer to the float layout for good
+            arm.grid.layer_devptr("laser")
+            assert arm.grid.layer_format("laser") != "coded"
         alg = [arm.algorithmic_bytes(c) for c in range(N_CYCLES)]
-        for w in range(12):
+        for w in range(warm):
             arm.step_dev(w)
         stream.synchronize()
         arm.ctx.profile_enable(True)
-        ms = timed_steps(torch, stream, arm.step_dev, 12, steps, arm)
+        arm.tile_stats()
+        ms = timed_steps(torch, stream, arm.step_dev, warm, steps, arm)
+        skipped, walked = arm.tile_stats()
         tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
+        kms = {n: arm.ctx.profile_read(n)[0] / max(arm.ctx.profile_read(n)[1], 1)
+               for n in ("himm_prep", "himm_tile", "vfh_update")}
         arm.ctx.profile_enable(False)
     peak = 6543.7
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", peak)
     except Exception:
         pass
-    used = float(np.mean([alg[(12 + k) % N_CYCLES][0] for k in range(steps)]))
+    used = float(np.mean([alg[(warm + k) % N_CYCLES][0] for k in range(steps)]))
     achieved = used / (tile_ms / max(tile_n, 1) / 1000.0) / 1e9
     out = {"workload": workload_config(name, 1, robots)["workload"], "value": robots * steps / (sum(ms) / 1000.0),
-           "unit": UNIT, "ms_per_step": sum(ms) / steps,
+           "unit": UNIT, "ms_per_step": sum(ms) / steps, "kernel_ms_per_step": kms,
+           "tile_items_per_launch": {"walked": walked / steps, "dropped_known_free": skipped / steps},
            "roofline": {"kernel": "himm_tile_coded_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "avg_launch_ms": tile_ms / max(tile_n, 1)}}
     del arm

@@ -40,6 +40,9 @@
 #include "move_control/map_provider.h"
 #include "move_control/map_updater.h"
 #include "move_control/steerer.h"
+#ifndef NAVH_DROPIN
+#include "move_control/laser_map_updater.h"
+#endif
 #undef private
 #undef protected
 
@@ -337,6 +340,74 @@ NAVH_API int navh_fleet_cycle(void** hs, int n, double t, const double* poses, c
   for (auto& th : pool) th.join();
   return threads;
 }
+
+#ifndef NAVH_DROPIN
+// Same cycle at the RangeSample boundary (the parity contract): the samples of every robot are put
+// straight into its LaserMapUpdater's buffer (what bufferIncomingMsg would have pushed, laser_map_updater.cpp:57-70)
+// - no thinning, every beam of the scan is applied, which is the workload the GPU arm runs - then
+// MapProvider::updateMap (updaters + master compose) and Steerer::update (submap copy, pseudo-scan, VFH) run as written.
+//   samples: 40-byte records {sx, sy, ex, ey (double), clear_end (int32), pad}; offsets: n + 1 ints
+NAVH_API int navh_fleet_cycle_samples(void** hs, int n, double t, const double* poses, const void* samples,
+                                      const int32_t* offsets, const double* goals, const double* speeds,
+                                      double* out_cmd, int threads) {
+  struct Rec {
+    double sx, sy, ex, ey;
+    int32_t clear_end, pad;
+  };
+  const Rec* recs = (const Rec*)samples;
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  auto work = [&](int lo, int hi) {
+    for (int r = lo; r < hi; ++r) {
+      Nav* nav = (Nav*)hs[r];
+      standin::Scope scope(&nav->world);
+      nav->world.now_ns = ros::Time(t).ns;
+      set_frame(nav, "base_link", poses[3 * r], poses[3 * r + 1], poses[3 * r + 2]);
+      move_control::LaserMapUpdater* laser = nullptr;
+      for (auto& u : nav->provider->mapUpdaters_)
+        if (u->typeName_ == "laser") laser = static_cast<move_control::LaserMapUpdater*>(u.get());
+      if (!laser) continue;
+      {
+        boost::unique_lock<boost::mutex> lock(laser->laserSampleBufferMutex_);
+        for (int i = offsets[r]; i < offsets[r + 1]; ++i) {
+          move_control::MapUpdater::RangeSample rs;
+          rs.start = grid_map::Position(recs[i].sx, recs[i].sy);
+          rs.end = grid_map::Position(recs[i].ex, recs[i].ey);
+          rs.ifClearEnd = recs[i].clear_end != 0;
+          laser->laserSampleBuffer_.push_back(rs);
+        }
+      }
+      nav->provider->updateMap();
+      nav_msgs::Odometry o;
+      o.twist.twist.linear.x = speeds ? speeds[r] : 0.0;
+      nav->world.publish<nav_msgs::Odometry>("/odom", o);
+      if (goals) { /* a fresh two-point plan every cycle: the steering target of this cycle */
+        std::vector<grid_map::Position> plan;
+        plan.push_back(grid_map::Position(poses[3 * r], poses[3 * r + 1]));
+        plan.push_back(grid_map::Position(goals[2 * r], goals[2 * r + 1]));
+        nav->steerer->acceptPlan(plan);
+      }
+      if (nav->steerer->ifPlanReady_) nav->steerer->update();
+      auto tw = nav->world.last_of<geometry_msgs::Twist>("/mobile_base/commands/velocity");
+      if (out_cmd) {
+        out_cmd[2 * r] = tw ? tw->linear.x : 0.0;
+        out_cmd[2 * r + 1] = tw ? tw->angular.z : 0.0;
+      }
+    }
+  };
+  if (threads == 1) {
+    work(0, n);
+    return 1;
+  }
+  std::vector<std::thread> pool;
+  for (int k = 0; k < threads; ++k) {
+    const int lo = (int)((long long)n * k / threads), hi = (int)((long long)n * (k + 1) / threads);
+    pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+  return threads;
+}
+#endif
 
 NAVH_API int navh_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 

@@ -59,6 +59,7 @@ def load(path):
     L.navh_fleet_cycle.argtypes = [vp, C.c_int, C.c_double, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float,
                                    C.c_float, vp, vp, vp, C.c_int]
     if not L.navh_is_dropin():
+        L.navh_fleet_cycle_samples.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp, vp, vp, C.c_int]
         L.navh_core_create.argtypes = [C.c_double] * 5 + [cp]
         L.navh_core_create.restype = vp
         L.navh_core_destroy.argtypes = [vp]
@@ -184,6 +185,25 @@ def fleet_cycle(nodes, t, poses, ranges, scan, goals=None, speeds=None, threads=
                        scan["angle_increment"], scan["range_min"], scan["range_max"],
                        g.ctypes.data if g is not None else None, s.ctypes.data if s is not None else None,
                        out.ctypes.data, int(threads))
+    return out
+
+
+def fleet_cycle_samples(nodes, t, poses, samples, offsets, goals=None, speeds=None, threads=1):
+    """navh_fleet_cycle_samples: every reference node applies its RangeSamples (oracle.SAMPLE_DTYPE records) and takes
+    one steering decision, robots block-partitioned over `threads` std::threads inside ONE native call."""
+    L = nodes[0].L
+    n = len(nodes)
+    hs = (C.c_void_p * n)(*[nd.h for nd in nodes])
+    poses = np.ascontiguousarray(poses, np.float64)
+    samples = np.ascontiguousarray(samples)
+    assert samples.dtype.itemsize == 40
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    out = np.zeros((n, 2), np.float64)
+    g = np.ascontiguousarray(goals, np.float64) if goals is not None else None
+    s = np.ascontiguousarray(speeds, np.float64) if speeds is not None else None
+    L.navh_fleet_cycle_samples(hs, n, float(t), poses.ctypes.data, samples.ctypes.data, offsets.ctypes.data,
+                               g.ctypes.data if g is not None else None, s.ctypes.data if s is not None else None,
+                               out.ctypes.data, int(threads))
     return out
 
 

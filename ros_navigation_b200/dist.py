@@ -108,6 +108,35 @@ class CommandExchange:
             from .capi import check, lib
             check(lib().b200nav_fleet_status(self.fleet), self.ctx.h)
 
+    def verify(self, slot):
+        """Driver-visible proof of the exchange (call outside timed regions, after wait(slot)): on every rank,
+        tables[slot] must be the concatenation of all ranks' rows of that cycle.  Each rank checksums the rows it
+        produced (position-weighted, so swapped rows or ranks show) and every rank's block of the table it received;
+        the per-block checksums of all ranks are gathered and compared with the producers' own.  Returns the number
+        of (receiver, block) pairs that differ - 0 when the exchange delivered everything everywhere."""
+        self.wait(slot)
+        dev = self.tables[slot].device
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+
+        def checksum(rows, first_row):
+            w = rows.contiguous().view(torch.int32).to(torch.int64).view(rows.shape[0], -1)
+            idx = torch.arange(first_row, first_row + rows.shape[0], device=rows.device, dtype=torch.int64)[:, None]
+            col = torch.arange(1, w.shape[1] + 1, device=rows.device, dtype=torch.int64)[None, :]
+            return (w * (idx * 4 + col)).sum().reshape(1)
+
+        own_rows = self.tables[slot][self.lo:self.hi] if self.push else self.locals[slot]
+        produced = checksum(own_rows, self.lo)
+        received = torch.cat([checksum(self.tables[slot][lo:hi], lo)
+                              for lo, hi in (partition(self.total, r, self.world) for r in range(self.world))])
+        if self.world == 1:
+            return int((received != produced).sum())
+        truth = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(truth, produced, group=self.group)
+        bad = (received != truth).sum().reshape(1)
+        dist.all_reduce(bad, op=dist.ReduceOp.SUM, group=self.group)
+        return int(bad)
+
     def close(self):
         if self.fleet is not None:
             from .capi import lib

@@ -72,6 +72,16 @@ def _worker(rank, world, port, total, out_dir):
                     t = ex.tables[prev].numpy().copy().view(COMMAND_DTYPE).reshape(-1)
                     assert np.array_equal(t["speed"], np.arange(total) + 1000 * (cycle - 1))
             ex.wait()
+            # verify(): the check bench.py runs at N > 1 - clean after a real gather, and it notices a damaged row,
+            # a stale cycle and two swapped rows on ANY rank
+            assert ex.verify(1) == 0 and ex.verify(0) == 0
+            if rank == 1:
+                ex.tables[1][0, 3] += 1
+            assert ex.verify(1) == 1
+            if rank == 1:
+                ex.tables[1][0, 3] -= 1
+                ex.tables[1][[0, 1]] = ex.tables[1][[1, 0]]
+            assert ex.verify(1) == (1 if D.owner_of(0, total, world) == D.owner_of(1, total, world) else 2)
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
