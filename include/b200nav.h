@@ -160,10 +160,16 @@ int b200nav_fleet_wait(b200nav_fleet* fleet, int slot);
  * waits (bounded, about a second) for all ranks' epochs, after which b200nav_fleet_table(slot) holds the whole fleet.
  * Setup: every rank calls _push_region (allocates its table + flags and returns a 64-byte CUDA IPC handle), the
  * launcher all-gathers the handles, every rank calls _push_connect with all of them (rank order).  Contract as
- * above: b200nav_fleet_wait(slot) before the update that writes slot again; at most one cycle per slot in flight. */
+ * above: b200nav_fleet_wait(slot) before the update that writes slot again; at most one cycle per slot in flight.
+ * Flow control: after its last read of b200nav_fleet_table(slot) a rank calls b200nav_fleet_release(slot) (enqueued on
+ * the context's stream, i.e. ordered after reads enqueued there); a rank's next update of that slot waits until every
+ * rank has released it, so a rank that runs ahead can never overwrite a table a slower rank is still reading.  An
+ * update whose caller did not release the slot releases it itself (correct, but ranks then run in lock step). */
 int b200nav_fleet_push_region(b200nav_fleet* fleet, int n_local, int n_total, int row0, uint8_t* handle64);
 int b200nav_fleet_push_connect(b200nav_fleet* fleet, const uint8_t* handles);
 void* b200nav_fleet_table(b200nav_fleet* fleet, int slot);
+/* slot < 0: both slots.  No-op for the NCCL exchange. */
+int b200nav_fleet_release(b200nav_fleet* fleet, int slot);
 /* Synchronises and reports (B200NAV_ERANGE) whether a wait of the peer push ran into its bound since the last call. */
 int b200nav_fleet_status(b200nav_fleet* fleet);
 int b200nav_fleet_destroy(b200nav_fleet* fleet);

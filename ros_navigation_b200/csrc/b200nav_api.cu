@@ -170,13 +170,14 @@ struct b200nav_fleet {
   cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
   bool pending[2] = {false, false};
   /* peer push (fused exchange): one IPC-shared region per rank = [2 slots][n_total commands] + [2 slots][world] flags
-   * + a block counter + an error word */
+   * + [2 slots][world] consumer acknowledgements + a block counter + an error word */
   bool push = false;
   int n_local = 0, n_total = 0, row0 = 0;
   uint8_t* region = nullptr;
   size_t region_bytes = 0;
   uint8_t* peer_region[B200NAV_MAX_PEERS] = {nullptr};
   unsigned long long epoch[2] = {0, 0};
+  unsigned long long released[2] = {0, 0}; /* last epoch of the slot this rank has acknowledged as consumed */
   bool push_pending[2] = {false, false};
   b200nav_command* table(int p, int slot) const {
     return reinterpret_cast<b200nav_command*>(peer_region[p]) + (size_t)slot * n_total;
@@ -185,9 +186,13 @@ struct b200nav_fleet {
     return reinterpret_cast<unsigned long long*>(peer_region[p] + sizeof(b200nav_command) * 2 * (size_t)n_total) +
            (size_t)slot * world;
   }
+  unsigned long long* acks(int p, int slot) const {
+    return reinterpret_cast<unsigned long long*>(peer_region[p] + sizeof(b200nav_command) * 2 * (size_t)n_total) +
+           (size_t)(2 + slot) * world;
+  }
   unsigned int* counter() const {
     return reinterpret_cast<unsigned int*>(region + sizeof(b200nav_command) * 2 * (size_t)n_total +
-                                           sizeof(unsigned long long) * 2 * (size_t)world);
+                                           sizeof(unsigned long long) * 4 * (size_t)world);
   }
   int* errword() const { return reinterpret_cast<int*>(counter() + 1); }
 };
@@ -1341,6 +1346,32 @@ int b200nav_fleet_wait(b200nav_fleet* f, int slot) {
   return B200NAV_OK;
 }
 
+/* Peer push: this rank has finished reading slot's table of the current epoch (everything enqueued so far on the
+ * context's stream).  Writers wait for it before they store the slot's next cycle. */
+static int fleet_release_slot(b200nav_fleet* f, int slot) {
+  if (!f->push || f->released[slot] >= f->epoch[slot]) return B200NAV_OK;
+  FleetAck a;
+  memset(&a, 0, sizeof(a));
+  for (int p = 0; p < f->world; p++) a.acks[p] = f->acks(p, slot);
+  a.world = f->world;
+  a.rank = f->rank;
+  a.epoch = f->epoch[slot];
+  fleet_release_kernel<<<1, 32, 0, f->ctx->stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(f->ctx, B200NAV_ECUDA, "fleet_release_kernel: %s", cudaGetErrorString(e));
+  f->released[slot] = f->epoch[slot];
+  return B200NAV_OK;
+}
+
+int b200nav_fleet_release(b200nav_fleet* f, int slot) {
+  if (!f || slot > 1) return B200NAV_EINVAL;
+  for (int s = (slot < 0 ? 0 : slot); s <= (slot < 0 ? 1 : slot); s++) {
+    const int rc = fleet_release_slot(f, s);
+    if (rc) return rc;
+  }
+  return B200NAV_OK;
+}
+
 int b200nav_fleet_push_region(b200nav_fleet* f, int n_local, int n_total, int row0, uint8_t* handle64) {
   if (!f || !handle64 || n_local < 1 || n_total < n_local || row0 < 0 || row0 + n_local > n_total ||
       f->world > B200NAV_MAX_PEERS)
@@ -1350,7 +1381,7 @@ int b200nav_fleet_push_region(b200nav_fleet* f, int n_local, int n_total, int ro
   f->n_local = n_local;
   f->n_total = n_total;
   f->row0 = row0;
-  f->region_bytes = sizeof(b200nav_command) * 2 * (size_t)n_total + sizeof(unsigned long long) * 2 * (size_t)f->world + 16;
+  f->region_bytes = sizeof(b200nav_command) * 2 * (size_t)n_total + sizeof(unsigned long long) * 4 * (size_t)f->world + 16;
   CUDA_TRY(ctx, cudaMalloc((void**)&f->region, f->region_bytes));
   CUDA_TRY(ctx, cudaMemset(f->region, 0, f->region_bytes));
   cudaIpcMemHandle_t h;
@@ -1405,6 +1436,15 @@ int b200nav_vfh_update_batched_dev_push(b200nav_vfh* v, b200nav_grid* g, const c
   push.world = f->world;
   push.rank = f->rank;
   push.row0 = f->row0;
+  if (f->epoch[slot] > 0) {
+    /* flow control: the slot's previous cycle must have been consumed by EVERY rank before its rows are overwritten.
+     * A caller that did not release the slot itself releases it here (its own reads are stream-ordered before). */
+    int rrc = fleet_release_slot(f, slot);
+    if (rrc) return rrc;
+    fleet_wait_acks_kernel<<<1, 32, 0, ctx->stream>>>(f->acks(f->rank, slot), f->world, f->epoch[slot], f->errword());
+    cudaError_t we = cudaGetLastError();
+    if (we != cudaSuccess) return set_err(ctx, B200NAV_ECUDA, "fleet_wait_acks_kernel: %s", cudaGetErrorString(we));
+  }
   push.epoch = ++f->epoch[slot];
   f->push_pending[slot] = true;
   int rc = vfh_launch(v, g, l, dev_in, nullptr, static_cast<b200nav_command*>(v->out_buf.p), 0, v->n_robots, nullptr, &push);

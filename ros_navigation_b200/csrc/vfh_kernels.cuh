@@ -87,6 +87,37 @@ __global__ void fleet_flag_kernel(const VfhPush push) {
   if (p < push.world) *reinterpret_cast<volatile unsigned long long*>(&push.flags[p][push.rank]) = push.epoch;
 }
 
+/* Flow control of the peer push.  A writer may only store cycle k+2's rows into a peer's table of slot s after that
+ * peer has finished READING the cycle-k table of slot s (publishing cycle k is not enough: a rank that runs ahead
+ * would tear the table under a slower reader).  Every rank therefore acknowledges, in every WRITER's ack array, the
+ * last epoch of the slot it has consumed (fleet_release_kernel, stream-ordered after its reads), and a writer waits
+ * for all acknowledgements of the previous epoch before its VFH+ kernel runs (fleet_wait_acks_kernel). */
+struct FleetAck {
+  unsigned long long* acks[B200NAV_MAX_PEERS]; /* ack array of rank p for this slot: [world], peer-mapped */
+  int world, rank;
+  unsigned long long epoch;
+};
+__global__ void fleet_release_kernel(const FleetAck a) {
+  const int p = threadIdx.x;
+  __threadfence_system();
+  if (p < a.world) *reinterpret_cast<volatile unsigned long long*>(&a.acks[p][a.rank]) = a.epoch;
+}
+__global__ void fleet_wait_acks_kernel(const unsigned long long* acks, int world, unsigned long long epoch, int* err) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    const volatile unsigned long long* f = acks + r;
+    long long spins = 0;
+    while (*f < epoch) {
+      __nanosleep(200);
+      if (++spins > 5000000ll) { /* about a second: a peer died or never released the slot */
+        *err = 2;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
 #define B200NAV_VFH_THREADS 128
 #define B200NAV_VFH_MAX_SECTORS 384 /* 360 / sector_angle, sector_angle >= 1 */
 #define B200NAV_NRANGES 361
