@@ -330,6 +330,8 @@ class GpuArm:
             return
         slot = i & 1
         if self.exchange.push:  # fused: the VFH+ kernel stores the commands into every rank's table itself
+            self.exchange.wait(1 - slot)      # the previous cycle's table is complete (a consumer would read it here)
+            self.exchange.release(1 - slot)   # ... and has been read: peers may write that slot again
             self.exchange.vfh_update_push(self.vfh, self.grid, "master", self.cyc.inputs[c], slot)
         else:
             self.exchange.wait(slot)  # the gather that last read this buffer has finished
@@ -388,6 +390,7 @@ class GpuArm:
                     self.exchange.gather_async(slot)
                 self.exchange.wait(slot)  # stream-side wait: the copy below follows the exchange
                 self.h_cmds[slot].copy_(self.exchange.tables[slot], non_blocking=True)
+                self.exchange.release(slot)  # peer push: the table has been read, peers may write the slot again
             tickets.append(self.ctx.fence())
             if k >= depth:
                 self.ctx.wait(tickets[k - depth])

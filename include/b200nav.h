@@ -349,6 +349,18 @@ int b200nav_vfh_update_batched_dev(b200nav_vfh* vfh, b200nav_grid* grid, const c
 int b200nav_vfh_update_batched_dev_push(b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
                                         const b200nav_vfh_input* dev_in, b200nav_fleet* fleet, int slot);
 
+/* Steerer::update's caller glue (move_control/src/steerer.cpp:221-258) for n robots, on the HOST (as in the
+ * reference; see ros_navigation_b200/csrc/steer_host.cpp for why): for every robot skip the waypoints of its plan
+ * that lie within `tolerance` mm (steerer.cpp:234-250, plan_index in/out; Steerer::acceptPlan starts it at 1) and fill
+ * inputs[r] with the pose, current_speed = (int)(odom_speed[r] * 1000) (:252,262), goal_distance = hypotf(dx, dy) in mm
+ * and goal_direction = RAD2DEG(normalize_angle_positive(atan2f(dy, dx) - yaw + pi/2)) (:254); `dt` is left alone.
+ *   poses: n*3 doubles (x, y, yaw: MapProvider::getRobotPos); waypoints: 2 doubles each, robot r owns
+ *   [wp_offsets[r], wp_offsets[r+1]); odom_speed: m/s or NULL; plan_done[r] = 1 when the plan is exhausted (the
+ *   reference then clears ifPlanReady_ and publishes nothing; inputs[r] gets goal_distance 0).  May be NULL. */
+int b200nav_steer_update_goals(int n, const double* poses, const double* waypoints, const int32_t* wp_offsets,
+                               int32_t* plan_index, float tolerance, const double* odom_speed,
+                               b200nav_vfh_input* inputs, uint8_t* plan_done);
+
 /* Read back per-robot state after an update (any pointer may be NULL):
  *  origin_hist / hist / last_binary: hist_size floats (VFH::OriginHist, VFH::Hist, Last_Binary_Hist);
  *  scalars[4] = {Picked_Angle, Last_Picked_Angle, Desired_Angle, Blocked_Circle_Radius};

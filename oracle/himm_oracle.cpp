@@ -142,11 +142,16 @@ inline bool index_limited_to_map_range(const oracle_geom* g, V2 start, V2 end, i
     d.y = d.y / n;
   }
   const double step = g->res - std::numeric_limits<double>::epsilon();
+  /* Defined answers where the reference's loop would not terminate (or only after millions of steps): a step that
+   * no longer moves the point, or more than 2^22 steps, mean "the ray never enters the map". */
+  int steps = 0;
   while (!geom_index(g, ns.x, ns.y, r, c)) {
+    const V2 before = ns;
     ns.x += step * d.x;
     ns.y += step * d.y;
+    if ((ns.x == before.x && ns.y == before.y) || ++steps > (1 << 22)) return false;
     const double ex = end.x - ns.x, ey = end.y - ns.y;
-    if (std::sqrt(ex * ex + ey * ey) < step) return false;
+    if (!(std::sqrt(ex * ex + ey * ey) >= step)) return false;
   }
   return true;
 }

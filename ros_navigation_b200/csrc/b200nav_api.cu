@@ -1109,6 +1109,8 @@ int b200nav_grid_set_geometry(b200nav_grid* g, int robot, double pos_x, double p
   if (!g || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
   if (start0 < 0 || start0 >= g->dims.rows || start1 < 0 || start1 >= g->dims.cols)
     return set_err(g->ctx, B200NAV_EINVAL, "start index (%d,%d) outside the buffer", start0, start1);
+  /* an asynchronous VFH+ update on the side stream may still read geom_dev[robot] for the previous cycle */
+  { int jrc = join_side(g->ctx); if (jrc) return jrc; }
   RobotGeom& rg = g->geom_host[robot];
   rg.pos_x = pos_x;
   rg.pos_y = pos_y;

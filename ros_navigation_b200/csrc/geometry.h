@@ -192,7 +192,11 @@ B200_HD void limit_position_to_range(double& px, double& py, double lx, double l
 }
 
 /* Pull a ray end into the map by stepping (res - eps) along the ray; iterative on purpose (the rounding of
- * the running sum is part of the reference result).  max_steps bounds the loop for hostile input. */
+ * the running sum is part of the reference result).  Two guards bound the loop for hostile input, where the
+ * reference (LineIterator.cpp:96-103) would spin: a step that no longer moves the point (coordinates beyond 2^53
+ * steps: the reference never terminates) and more than B200NAV_CLIP_MAX_STEPS steps (a start hundreds of kilometres
+ * from the map: the reference would get there eventually) both give "no line" (defined answers). */
+#define B200NAV_CLIP_MAX_STEPS (1 << 22)
 B200_HD bool clip_into_map(const GridDims& d, const RobotGeom& g, double sx, double sy, double ex, double ey, int& r,
                            int& c) {
   /* Common case first: the end is inside the map and the direction (sqrt + two divisions) is never needed. */
@@ -206,9 +210,12 @@ B200_HD bool clip_into_map(const GridDims& d, const RobotGeom& g, double sx, dou
     dy = dy / n;
   }
   const double step = d.res - B200NAV_DBL_EPSILON;
+  int steps = 0;
   do {
+    const double px = nx, py = ny;
     nx += step * dx;
     ny += step * dy;
+    if ((nx == px && ny == py) || ++steps > B200NAV_CLIP_MAX_STEPS) return false; /* no progress / too far away */
     const double qx = ex - nx, qy = ey - ny;
     if (!(sqrt(qx * qx + qy * qy) >= step)) return false; /* also ends the loop on NaN */
   } while (!grid_index(d, g, nx, ny, r, c));

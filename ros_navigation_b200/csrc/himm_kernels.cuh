@@ -266,7 +266,7 @@ __device__ __forceinline__ float himm_mark(float v) {
  * K1: tile-owner update kernel.  One WARP (= one CTA of 32 threads) owns one SUB x SUB tile of one robot's grid.
  *
  * Cell storage in shared memory: HIMM values live in the closed set {NaN, 0, 10, ..., 180} (clearCell / markCell map
- * the set into itself), so a staged tile holds one BYTE per cell: code = value/10 (0..18), 19 = NaN.  That is 4x less
+ * the set into itself), so a staged tile holds one BYTE per cell: code 0 = NaN, code k = value/10 + 1 (cells.cuh).  That is 4x less
  * shared memory than floats => ~26 resident warps per SM instead of 10, which is what hides the dependent
  * LDS -> op -> STS latency of the in-order walk.  Tiles are converted on load / store (float layers in HBM keep the
  * grid_map layout).  A tile that holds any other value (foreign data uploaded by the host) is processed by the same

@@ -102,6 +102,14 @@ class CommandExchange:
               self.ctx.h)
         self._pending[slot] = True
 
+    def release(self, slot):
+        """Peer push only: this rank has finished reading tables[slot] (reads enqueued on the context's stream so
+        far).  Lets the other ranks start the slot's next cycle; without it the next vfh_update_push releases the slot
+        itself, which keeps the ranks in lock step."""
+        if self.push:
+            from .capi import check, lib
+            check(lib().b200nav_fleet_release(self.fleet, slot), self.ctx.h)
+
     def status(self):
         """Synchronise and raise if a peer-push wait timed out since the last call."""
         if self.fleet is not None:

@@ -38,6 +38,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 lines = ["# ncu summaries, tag %s" % tag, ""]
 traffic = {}
+issue = {}
 for kern in ("tile", "prep", "vfh"):
     rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (kern, tag))
     if not os.path.exists(rep):
@@ -56,6 +57,8 @@ for kern in ("tile", "prep", "vfh"):
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
             return fl(v) * mult
         traffic["c4"] = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
+        issue["c4"] = {"warp_instructions_per_launch": fl(m["smsp__inst_executed.sum"][0]),
+                       "source": "ncu smsp__inst_executed.sum, profiles/ncu_summary_%s.md (tile kernel, one launch)" % tag}
     # stall reasons
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
@@ -96,6 +99,12 @@ if traffic:
     old = json.load(open(tj)) if os.path.exists(tj) else {}
     old.update(traffic)
     json.dump(old, open(tj, "w"), indent=1)
+
+if issue:
+    ij = os.path.join(P, "issue.json")
+    old = json.load(open(ij)) if os.path.exists(ij) else {}
+    old.update(issue)
+    json.dump(old, open(ij, "w"), indent=1)
 
 # launch list
 lc = os.path.join(G, "launches_%s.csv" % tag)

@@ -71,6 +71,28 @@ with torch.cuda.stream(stream):
         stream.synchronize()
         assert torch.equal(push.tables[slot], plain.tables[slot]), (cycle, rank)
     push.status()
+    # Rank skew (ADVICE r1): rank 1 is slow to READ each table (a long spin kernel sits between its wait and its read),
+    # rank 0 runs ahead as fast as it can.  Every cycle's decision carries the cycle number (empty map: the picked
+    # angle is the goal direction), so a table that a faster writer tore shows rows of a later cycle.
+    empty = DeviceGridMap(ctx, (6.4, 6.4), 0.05, n_robots=n_local, layers=("master",))
+    vs = VFH(ctx, n_robots=n_local)
+    snaps = []
+    for cycle in range(12):
+        slot = cycle & 1
+        inp = np.zeros(n_local, capi.VFH_INPUT_DTYPE)
+        inp["dt"], inp["goal_direction"], inp["goal_distance"], inp["goal_tolerance"] = 0.2, 10.0 + cycle, 2500.0, 250.0
+        d_in = torch.from_numpy(inp.view(np.uint8).reshape(n_local, -1)).to(dev)
+        push.vfh_update_push(vs, empty, "master", d_in, slot)
+        push.wait(slot)
+        if rank == 1:
+            torch.cuda._sleep(int(2e8))          # ~0.1 s on the context's stream before the table is read
+        snaps.append(push.tables[slot].clone())  # the read, stream-ordered after the wait (and the sleep)
+        push.release(slot)
+    stream.synchronize()
+    for cycle, snap in enumerate(snaps):
+        got = snap.cpu().numpy().view(capi.COMMAND_DTYPE).reshape(-1)["picked_angle"]
+        assert np.all(got == np.float32(10.0 + cycle)), (rank, cycle, np.unique(got))
+    push.status()
     push.close(); plain.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -210,3 +210,40 @@ def test_sonar_rays_and_moving_map_match_reference():
     occ = node.occupancy()
     assert np.array_equal(occ, O.to_occupancy(g, master))
     node.close()
+
+
+def test_steer_goal_glue_matches_reference_steerer():
+    """b200nav_steer_update_goals (the product's host-side restatement of Steerer::update's caller glue,
+    steerer.cpp:228-256: waypoint advance, desiredDist, desiredAngle, odometry speed) against the reference's own
+    Steerer::update on a multi-waypoint plan, until the plan is exhausted."""
+    from ros_navigation_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(5)
+    node = N.Node(N.REF_PATH, 10.0, 10.0, False, t0=1.0)
+    plan = np.array([[0, 0], [0.5, 0.2], [0.6, 0.25], [2.0, 1.0], [2.1, 1.1], [1.0, 2.0]], float)
+    node.accept_plan(plan)
+    idx, offs = np.array([1], np.int32), np.array([0, len(plan)], np.int32)
+    inp, done = np.zeros(1, capi.VFH_INPUT_DTYPE), np.zeros(1, np.uint8)
+    pos, leg, compared = np.zeros(2), 1, 0
+    for step in range(2000):
+        if leg < len(plan):   # walk towards the current waypoint with some wobble
+            d = plan[leg] - pos
+            pos = pos + 0.02 * d / max(np.hypot(*d), 1e-9) + rng.uniform(-0.004, 0.004, 2)
+            if np.hypot(*(plan[leg] - pos)) < 0.2:
+                leg += 1
+        yaw, v = rng.uniform(-3.1, 3.1), rng.uniform(0, 0.3)
+        node.set_time(1.0 + 0.2 * (step + 1))
+        node.set_frame("base_link", pos[0], pos[1], yaw)
+        node.publish_odom(v)
+        out, rp = node.steer(), node.robot_pose()
+        poses, speed = np.array([[rp[0], rp[1], rp[2]]]), np.array([v])
+        assert L.b200nav_steer_update_goals(1, poses.ctypes.data, plan.ctypes.data, offs.ctypes.data, idx.ctypes.data,
+                                            250.0, speed.ctypes.data, inp.ctypes.data, done.ctypes.data) == 0
+        assert bool(done[0]) == (not out["plan_ready"]), step
+        if done[0]:
+            break
+        assert np.float32(inp["goal_direction"][0]) == np.float32(out["desired_angle"]), step
+        assert int(inp["current_speed"][0]) == int(v * 1000.0)
+        compared += 1
+    assert done[0] == 1 and compared > 100 and idx[0] == len(plan)
+    node.close()
