@@ -415,6 +415,17 @@ class GpuArm:
         return 8 * visits + 8 * marks + 36 * beams, visits, marks, beams
 
 
+def tile_phase(ctx):
+    """Device time of the tile walk of an update = the multi-warp kernel for the heavy (origin) tiles plus the
+    one-warp kernel for the rest, back to back on one stream.  Returns (summed ms, number of updates, parts)."""
+    one_ms, one_n = ctx.profile_read("himm_tile")
+    mw_ms, mw_n = ctx.profile_read("himm_tile_mw")
+    parts = {"himm_tile_coded_kernel": one_ms / max(one_n, 1)}
+    if mw_n:
+        parts["himm_tile_coded_mw_kernel"] = mw_ms / mw_n
+    return one_ms + mw_ms, one_n, parts
+
+
 def flush_l2_light(arm):
     """In-stream flush for the pipelined end-to-end loop: write a buffer larger than L2 (160 MiB > 126 MB).  The
     write-back of these lines happens inside the timed region like everything else there."""
@@ -491,7 +502,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         wall = time.perf_counter() - t_wall0
         launches = arm.ctx.launches - launches0
         tiles_skipped, tiles_processed = arm.tile_stats()
-        tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
+        tile_ms, tile_n, tile_parts = tile_phase(arm.ctx)
         prep_ms, prep_n = arm.ctx.profile_read("himm_prep")
         vfh_ms, vfh_n = arm.ctx.profile_read("vfh_update")
         arm.ctx.profile_enable(False)
@@ -570,7 +581,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "l2_flush_ms_per_step": flush_s * 1000.0 / args.steps},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "himm_tile_coded_kernel", "achieved": achieved, "peak": hbm_peak,
+        "roofline": {"bound": "hbm", "kernel": "tile walk = " + " + ".join(sorted(tile_parts)), "achieved": achieved,
+                     "peak": hbm_peak, "kernel_parts_ms": tile_parts,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "avg_launch_ms": tile_avg_ms, "launches_timed": int(tile_n),
@@ -662,11 +674,15 @@ def cold_grid_numbers(torch, stream, arm, robots_total, alg, hbm_peak):
             arm.exchange.wait()
         arm.grid.clear("laser")
         stream.synchronize()
+        if arm.world > 1:   # ranks reach this point at different times; a step's events include the exchange
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
         arm.ctx.profile_enable(True)
         arm.tile_stats()
         ms = timed_steps(torch, stream, arm.step_dev, 0, N_CYCLES, arm)
         skipped, walked = arm.tile_stats()
-        tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
+        tile_ms, tile_n, _ = tile_phase(arm.ctx)
         arm.ctx.profile_enable(False)
     t = torch.tensor([float(sum(ms))], dtype=torch.float64, device=arm.cyc.device)
     if arm.world > 1:
@@ -752,7 +768,7 @@ def single_robot_numbers(device, name, scans=300):
     with torch.cuda.stream(stream):
         for k in range(50):
             arm.step_dev(k)
-    kms = {n: arm.ctx.profile_read(n)[0] / 50.0 for n in ("himm_prep", "himm_tile", "vfh_update")}  # ms per scan
+    kms = {n: arm.ctx.profile_read(n)[0] / 50.0 for n in ("himm_prep", "himm_tile", "himm_tile_mw", "vfh_update")}  # ms per scan
     arm.ctx.profile_enable(False)
     return {"workload": workload_config(name, 1, 1)["workload"], "value": scans / (dev_ms / 1000.0),
             "e2e": scans / e2e_s, "unit": UNIT, "ms_per_scan": dev_ms / scans, "kernel_ms": kms,
@@ -780,9 +796,10 @@ def batched_numbers(device, name, steps=12, warm=12, float_layers=False):
         arm.tile_stats()
         ms = timed_steps(torch, stream, arm.step_dev, warm, steps, arm)
         skipped, walked = arm.tile_stats()
-        tile_ms, tile_n = arm.ctx.profile_read("himm_tile")
-        kms = {n: arm.ctx.profile_read(n)[0] / max(arm.ctx.profile_read(n)[1], 1)
-               for n in ("himm_prep", "himm_tile", "vfh_update")}
+        tile_ms, tile_n, tile_parts = tile_phase(arm.ctx)
+        kms = {n: arm.ctx.profile_read(n)[0] / max(arm.ctx.profile_read(n)[1], 1) for n in ("himm_prep", "vfh_update")}
+        kms["himm_tile"] = tile_ms / max(tile_n, 1)
+        kms.update(tile_parts)
         arm.ctx.profile_enable(False)
     peak = 6543.7
     try:

@@ -70,7 +70,7 @@ int64_t b200nav_ctx_launch_count(b200nav_ctx* ctx);
 /* Per-kernel device timing with CUDA events on the context's stream (observability; the reference has only a
  * loop-overrun warning, map_provider.cpp:170-173).  enable != 0 starts recording and resets the counters.
  * b200nav_ctx_profile_read synchronises the stream and returns, for kernel `name` ("himm_prep", "himm_tile",
- * "vfh_update"), the summed device time in milliseconds and the number of timed launches. */
+ * "himm_tile_mw", "vfh_update"), the summed device time in milliseconds and the number of timed launches. */
 int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable);
 int b200nav_ctx_profile_read(b200nav_ctx* ctx, const char* name, double* total_ms, int64_t* launches);
 

@@ -33,8 +33,8 @@ using namespace b200nav;
  * ============================================================================================================== */
 
 /* Event-pair pool for per-kernel device timing (b200nav_ctx_profile_*). */
-enum { PROF_HIMM_PREP = 0, PROF_HIMM_TILE = 1, PROF_VFH = 2, PROF_KINDS = 3 };
-static const char* const kProfNames[PROF_KINDS] = {"himm_prep", "himm_tile", "vfh_update"};
+enum { PROF_HIMM_PREP = 0, PROF_HIMM_TILE = 1, PROF_VFH = 2, PROF_HIMM_TILE_MW = 3, PROF_KINDS = 4 };
+static const char* const kProfNames[PROF_KINDS] = {"himm_prep", "himm_tile", "vfh_update", "himm_tile_mw"};
 struct ProfSlot {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs; /* recorded, not yet read */
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_pairs;
@@ -506,6 +506,7 @@ int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int 
 }
 
 constexpr int kHeavyWarps = 4; /* warps per CTA of the multi-warp heavy-tile kernel */
+constexpr int kMwAllRobots = 32; /* fleets up to this size: every tile item on a multi-warp CTA */
 
 int himm_launch_tile(b200nav_grid* g, const HimmArgs& a_in) {
   b200nav_ctx* ctx = g->ctx;
@@ -514,20 +515,21 @@ int himm_launch_tile(b200nav_grid* g, const HimmArgs& a_in) {
   HimmArgs a = a_in;
   a.skip_heavy = 0;
   const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
-  /* Experimental (B200NAV_MW_HEAVY=1): the tile that holds a scan's own origin sees every beam and keeps ONE warp
-   * busy for most of a single-robot update - give those items to CTAs of kHeavyWarps warps that split the rings of
-   * the tile among them; the one-warp kernel takes the rest.  Exact (tests/test_layer_formats_gpu.py runs the HIMM
-   * suite with it), but run back to back with the one-warp kernel it does not pay yet (C2: 0.079 ms instead of
-   * 0.057 ms for the tile phase): it needs its own stream next to the light items, see DESIGN.md section 7. */
+  /* The tile that holds a scan's own origin sees every beam of the scan: walked by one warp it is the critical path
+   * of a small update (a single robot: 0.057 of 0.095 ms per scan).  A fleet of up to kMwAllRobots robots cannot fill
+   * the GPU with one warp per tile anyway: there every touched tile gets a CTA of kHeavyWarps warps that share the
+   * tile as a wavefront pipeline over the beam batches (himm_tile_coded_mw_kernel / himm_apply_list_pipe: no
+   * replicated work) and the one-warp kernel is not launched.  Large fleets are throughput bound and keep one warp
+   * per tile (measured: multi-warp CTAs for the heavy items of 1024 robots cost 0.33 instead of 0.28 ms per cycle).
+   * B200NAV_MW_HEAVY=0: one warp per tile always; =2: multi-warp CTAs always (A/B aid). */
   static const char* mw_env = getenv("B200NAV_MW_HEAVY");
-  const bool use_mw = a.coded && mw_env && atoi(mw_env) != 0;
-  if (use_mw) {
-    ProfScope ps(ctx, PROF_HIMM_TILE);
-    const unsigned blocks = (unsigned)std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count);
+  const int mw_mode = mw_env ? atoi(mw_env) : 1;
+  a.mw_all = (a.coded && (mw_mode == 2 || (mw_mode == 1 && a.n_active <= kMwAllRobots))) ? 1 : 0;
+  if (a.mw_all) {
+    ProfScope ps(ctx, PROF_HIMM_TILE_MW);
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * 8));
     himm_tile_coded_mw_kernel<kListCap, kHeavyWarps><<<blocks, 32 * kHeavyWarps, smem, ctx->stream>>>(a);
-    int rc = check_launch(ctx, "himm_tile_coded_mw_kernel");
-    if (rc) return rc;
-    a.skip_heavy = 1;
+    return check_launch(ctx, "himm_tile_coded_mw_kernel");
   }
   /* persistent: as many one-warp CTAs as can be resident (32 per SM), never more than there are tiles */
   dim3 grid((unsigned)std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * 32));

@@ -85,6 +85,7 @@ struct HimmArgs {
   int chunk_beams;                /* beams per chunk: multiple of 32, <= HIMM_CHUNK */
   int mask_words;                 /* chunk_beams / 32                              */
   int skip_heavy;                 /* the one-warp tile kernel leaves the heavy items to himm_tile_coded_mw_kernel */
+  int mw_all;                     /* small fleets: himm_tile_coded_mw_kernel takes EVERY item (no one-warp launch) */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -1014,6 +1015,255 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Multi-warp walk of ONE tile's beam list: a wavefront pipeline over the batches.
+ *
+ * The tile that holds a scan's own origin sees every beam of the scan; walked by one warp it is the critical path of
+ * an update.  Here the NW warps of a CTA share the tile: warp w owns batches w, w + NW, w + 2 NW, ... of the ordered
+ * beam list and walks each of them exactly as the one-warp kernel does (same set-up, same ring blocks, same exact
+ * path) - no work is replicated.  What the reference's order demands is only that, cell by cell, batch j is applied
+ * after batch j - 1.  For fan batches that share their origin cell a cell at step t of a line has Chebyshev distance
+ * t from the origin, so batch j may enter the block of steps [ts, ts + 4) as soon as batch j - 1 has left it: every
+ * warp publishes its progress (batch number, origin, steps completed) in one 64-bit shared-memory word and its
+ * successor waits on that word before each block - a systolic wavefront, batch j one block behind batch j - 1.  If
+ * the two batches differ in origin, or either of them is not a fan (general schedule), the successor waits until its
+ * predecessor has finished.  The set-up of a batch does not touch the tile and runs ahead of the predecessor's walk.
+ *   progress word: (batch + 1) << 48 | steps_done << 32 | origin   (steps_done = 0xffff: finished; origin = ~0: no fan)
+ * ------------------------------------------------------------------------------------------------------------- */
+#define HIMM_PIPE_DONE 0xffffull
+#define HIMM_PIPE_NOFAN 0xffffffffull
+
+__device__ __forceinline__ unsigned long long pipe_load(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void pipe_store(uint32_t addr, unsigned long long v) {
+  asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+template <int NW>
+__device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const int pitch,
+                                                     const BeamSeg* __restrict__ segs, const uint16_t* list,
+                                                     const int n_list, const int R0, const int R1, const int C0,
+                                                     const int C1, const int lane, const int warp,
+                                                     const uint32_t prog /* shared address of NW progress words */) {
+  constexpr int RINGS = 4;
+  const uint32_t my_word = prog + 8u * (uint32_t)warp, pred_word = prog + 8u * (uint32_t)((warp + NW - 1) % NW);
+  BeamSeg nb;
+  nb.r0 = -1;
+  nb.mr = -1;
+  if (32 * warp + lane < n_list) nb = segs[list[32 * warp + lane]];
+  for (int j0 = 32 * warp; j0 < n_list; j0 += 32 * NW) {
+    const int jb = j0 >> 5; /* batch number */
+    const int j = j0 + lane;
+    const BeamSeg b = nb;
+    const bool have = j < n_list;
+    nb.r0 = -1;
+    nb.mr = -1;
+    if (j + 32 * NW < n_list) nb = segs[list[j + 32 * NW]];
+    /* ---- set-up (as himm_apply_list) ---- */
+    int my_len = 0, my_t0 = 0, my_off0 = view.bias(), my_rem0 = 0, my_dm = 0, my_dn = 0, my_add = 0, my_den = 1, my_moff = -1;
+    int my_r0 = -1, my_c0 = -1, my_q0 = 0;
+    unsigned my_S = 0u, my_B = 0u;
+    bool my_diag = false, mark_at_end = false;
+    if (have) {
+      const bool has_mark = b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1;
+      if (has_mark) my_moff = view.bias() + (b.mc - C0) * pitch + (b.mr - R0);
+      if (b.r0 >= 0) {
+        const LineForm f = line_form(b);
+        int t0, t1;
+        if (clip_line_to_rect(f, R0, R1, C0, C1, t0, t1)) {
+          const unsigned den = (unsigned)max(f.den, 1);
+          dda_init((unsigned)f.add, den, my_S, my_B, my_diag);
+          const unsigned x0 = (unsigned)(f.den >> 1) + (unsigned)t0 * (unsigned)f.add;
+          const unsigned q0 = my_diag ? (unsigned)t0 : (unsigned)(dda_at(my_S, my_B, (unsigned)t0) >> 32);
+          my_q0 = my_diag ? 0 : (int)q0;
+          my_rem0 = (int)(x0 - q0 * den);
+          const int mj = f.m0 + f.sm * t0, mn = f.n0 + f.sn * (int)q0;
+          const int r = f.row_major ? mj : mn, c = f.row_major ? mn : mj;
+          my_off0 = view.bias() + (c - C0) * pitch + (r - R0);
+          my_dm = f.row_major ? f.sm : f.sm * pitch;
+          my_dn = f.row_major ? f.sn * pitch : f.sn;
+          my_add = f.add;
+          my_den = (int)den;
+          my_len = t1 - t0 + 1;
+          my_t0 = t0;
+          my_r0 = b.r0;
+          my_c0 = b.c0;
+          mark_at_end = has_mark && t1 == f.den && b.r1 == b.mr && b.c1 == b.mc;
+        }
+      }
+    }
+    const bool has_work = my_len > 0 || my_moff >= 0;
+    unsigned active = __ballot_sync(0xffffffffu, has_work);
+    const unsigned long long tag = (unsigned long long)(jb + 1) << 48;
+    bool fan = false;
+    unsigned long long origin = HIMM_PIPE_NOFAN;
+    if (active != 0u) {
+      const int lead = __ffs(active) - 1;
+      const int lr0 = __shfl_sync(0xffffffffu, my_r0, lead), lc0 = __shfl_sync(0xffffffffu, my_c0, lead);
+      const bool lane_ok = !has_work || (my_len > 0 && my_r0 == lr0 && my_c0 == lc0 && (my_moff < 0 || mark_at_end));
+      fan = __all_sync(0xffffffffu, lane_ok);
+      if (fan) origin = (unsigned long long)(unsigned)(lr0 * 65536 + lc0);
+    }
+    /* "Finished" is a statement about the whole chain: batch jb may only say it once batch jb - 1 has (a batch that
+     * covers few steps, or none, must not let its successor overtake an earlier, longer batch). */
+    auto wait_pred_finished = [&]() {
+      if (jb == 0) return;
+      unsigned long long p;
+      do {
+        p = pipe_load(pred_word);
+      } while ((p >> 48) < (unsigned long long)jb ||
+               ((p >> 48) == (unsigned long long)jb && ((p >> 32) & 0xffffull) != HIMM_PIPE_DONE));
+    };
+    /* announce the batch (nothing done yet) */
+    if (lane == 0) pipe_store(my_word, tag | origin);
+    if (active == 0u) { /* an empty batch only passes the chain's state on */
+      wait_pred_finished();
+      if (lane == 0) pipe_store(my_word, tag | (HIMM_PIPE_DONE << 32) | origin);
+      continue;
+    }
+    /* ---- dependency on batch jb - 1 (owned by the previous warp) ---- */
+    bool pred_done = jb == 0;    /* nothing (more) to wait for */
+    unsigned pred_steps = 0u;    /* steps [0, pred_steps) of the predecessor are complete (same origin, both fans) */
+    if (!pred_done) {
+      unsigned long long p;
+      do {
+        p = pipe_load(pred_word);
+      } while ((p >> 48) < (unsigned long long)jb); /* batch jb - 1 not announced yet */
+      if ((p >> 48) > (unsigned long long)jb || ((p >> 32) & 0xffffull) == HIMM_PIPE_DONE) {
+        pred_done = true;
+      } else if (!fan || (p & 0xffffffffull) != origin) {
+        do { /* other origin, or one of us is no fan: any cell may be shared at any step */
+          p = pipe_load(pred_word);
+        } while ((p >> 48) == (unsigned long long)jb && ((p >> 32) & 0xffffull) != HIMM_PIPE_DONE);
+        pred_done = true;
+      } else {
+        pred_steps = (unsigned)((p >> 32) & 0xffffull);
+      }
+      __threadfence_block();
+    }
+    if (fan) {
+      const int first = (my_len > 0) ? my_t0 : 0x7fffffff;
+      const unsigned span = (my_len > 0) ? (unsigned)(my_len - 1) : 0u;
+      const int last = (my_len > 0) ? my_t0 + my_len - 1 : -0x7fffffff;
+      const int tmin = __reduce_min_sync(0xffffffffu, first), tmax = __reduce_max_sync(0xffffffffu, last);
+      const int step_plain = my_diag ? my_dm + my_dn : my_dm, step_carry = step_plain + my_dn;
+      const int mark_k = (my_moff >= 0) ? (int)span : -1;
+      const int back = (my_len > 0) ? my_t0 - tmin : 0;
+      const unsigned long long xs = dda_at(my_S, my_B, (unsigned)((my_len > 0) ? tmin : 0));
+      unsigned frac = (unsigned)xs;
+      const int qs = my_diag ? 0 : (int)(xs >> 32);
+      int off = my_off0 - back * step_plain - (my_q0 - qs) * my_dn;
+      int k = (my_len > 0) ? tmin - first : -0x40000000;
+      const int n_iter = (tmax - tmin) / RINGS;
+      for (int i = 0; i <= n_iter; i++, k += RINGS) {
+        const unsigned need = (unsigned)(tmin + RINGS * (i + 1)); /* my block covers steps < need */
+        if (!pred_done && pred_steps < need) {
+          unsigned long long p;
+          for (;;) {
+            p = pipe_load(pred_word);
+            if ((p >> 48) > (unsigned long long)jb || ((p >> 32) & 0xffffull) == HIMM_PIPE_DONE) {
+              pred_done = true;
+              break;
+            }
+            pred_steps = (unsigned)((p >> 32) & 0xffffull);
+            if (pred_steps >= need) break;
+          }
+          __threadfence_block();
+        }
+        /* one block of RINGS steps: identical to himm_apply_list's ring_block */
+        int offs[RINGS];
+        bool hot[RINGS];
+        bool sens = mark_k >= 0 && (unsigned)(mark_k - k) < (unsigned)RINGS;
+#pragma unroll
+        for (int r = 0; r < RINGS; r++) {
+          offs[r] = off;
+          const bool on = (unsigned)(k + r) <= span;
+          hot[r] = on && view.sensitive(off);
+          sens = sens || hot[r];
+          const unsigned nf = frac + my_S;
+          off += (nf < frac) ? step_carry : step_plain;
+          frac = nf;
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, sens)) {
+#pragma unroll
+          for (int r = 0; r < RINGS; r++)
+            if ((unsigned)(k + r) <= span) view.set_free(offs[r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < RINGS; r++) {
+            const bool on = (unsigned)(k + r) <= span, marking = k + r == mark_k;
+            if (__any_sync(0xffffffffu, hot[r] || (on && marking))) {
+              const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1 - lane);
+              const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
+              if (on && (group & ((1u << lane) - 1u)) == 0u) {
+                if (marks == 0u) view.clear_n(offs[r], __popc(group), false);
+                else view.clear_seq(offs[r], group, marks);
+              }
+            } else if (on) {
+              view.set_free(offs[r]);
+            }
+          }
+        }
+        /* publish: every step below `need` of this batch is complete (the last block publishes "finished" below) */
+        if (i < n_iter) {
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) pipe_store(my_word, tag | ((unsigned long long)min(need, 0xfffeu) << 32) | origin);
+        }
+      }
+      __syncwarp();
+    } else {
+      /* ---- general schedule (the predecessor has finished): one beam at a time, lanes striding over its cells ---- */
+      while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        const int len = __shfl_sync(0xffffffffu, my_len, src);
+        const int moff = __shfl_sync(0xffffffffu, my_moff, src);
+        if (len > 0) {
+          const int off0 = __shfl_sync(0xffffffffu, my_off0, src);
+          const int rem0 = __shfl_sync(0xffffffffu, my_rem0, src);
+          const int dm = __shfl_sync(0xffffffffu, my_dm, src);
+          const int dn = __shfl_sync(0xffffffffu, my_dn, src);
+          const int add = __shfl_sync(0xffffffffu, my_add, src);
+          const int den = __shfl_sync(0xffffffffu, my_den, src);
+          const float rcp = __frcp_rn((float)den);
+          const int x = rem0 + lane * add;
+          const int q = small_quotient(x, rcp);
+          int rem = x - q * den;
+          int off = off0 + lane * dm + q * dn;
+          const int x32 = 32 * add;
+          const int q32 = small_quotient(x32, rcp);
+          const int r32 = x32 - q32 * den;
+          const int step = 32 * dm + q32 * dn;
+          for (int kk = lane; kk < len; kk += 32) {
+            view.clear_n(off, 1, false);
+            rem += r32;
+            off += step;
+            if (rem >= den) {
+              rem -= den;
+              off += dn;
+            }
+          }
+          __syncwarp();
+        }
+        if (moff >= 0) {
+          if (lane == 0) view.mark(moff);
+          __syncwarp();
+        }
+      }
+    }
+    /* finished (and so is everything before me): successors may touch any cell */
+    if (!pred_done) wait_pred_finished();
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) pipe_store(my_word, tag | (HIMM_PIPE_DONE << 32) | origin);
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
  * K1 for the "heavy" work items (the tile that holds a scan's own origin sees every beam of it) when there are few
  * robots: NW warps share one tile (see himm_apply_list<View, NW>), which cuts the latency of the longest item of a
  * single-robot update.  CTA b handles heavy items b, b + gridDim.x, ...; the one-warp kernel then only takes the
@@ -1027,6 +1277,7 @@ __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a)
   uint16_t* list = reinterpret_cast<uint16_t*>(himm_smem_raw + HIMM_TILE_BYTES);
   __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ int s_nlist;
+  __shared__ __align__(8) unsigned long long s_prog[NW]; /* pipeline progress words (himm_apply_list_pipe) */
 
   uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
   asm volatile("mov.u32 %0, %0;" : "+r"(tile_saddr));
@@ -1035,6 +1286,8 @@ __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a)
   const int rows = a.dims.rows, cols = a.dims.cols;
   const int n_tiles = a.tiles_r * a.tiles_c;
   const int n_heavy = *reinterpret_cast<volatile int*>(&a.counters[0]);
+  const int n_items = a.mw_all ? n_heavy + *reinterpret_cast<volatile int*>(&a.counters[3]) : n_heavy;
+  const uint32_t prog = (uint32_t)__cvta_generic_to_shared(&s_prog[0]);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1042,8 +1295,8 @@ __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a)
   __syncthreads();
   uint32_t phase = 0;
 
-  for (int item = blockIdx.x; item < n_heavy; item += gridDim.x) {
-    const int rt = a.worklist[item];
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int rt = a.worklist[item < n_heavy ? item : a.worklist_cap - 1 - (item - n_heavy)];
     const int rel = rt / n_tiles, tile_id = rt - rel * n_tiles;
     const int robot = a.robot0 + rel;
     const int tile_r = tile_id % a.tiles_r, tile_c = tile_id / a.tiles_r;
@@ -1088,6 +1341,7 @@ __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a)
         pos = tot0 + inc1 - p1;
         for (uint32_t ww = w1; ww; ww &= ww - 1) list[pos++] = (uint16_t)(32 * (lane + 32) + __ffs(ww) - 1);
         if (lane == 0) s_nlist = n;
+        if (lane < NW) s_prog[lane] = 0ull; /* no batch of this list announced yet */
       }
       __syncthreads();
       const int n_list = s_nlist;
@@ -1099,7 +1353,7 @@ __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a)
         }
         if (threadIdx.x == 0) atomicAdd(&a.counters[5], 1); /* statistics: tiles processed */
         const BeamSeg* segs = a.segs + beg + chunk * a.chunk_beams;
-        himm_apply_list<CodeView, NW>(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane, warp);
+        himm_apply_list_pipe<NW>(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane, warp, prog);
       }
       __syncthreads(); /* all warps are done with the list (and with the tile, after the last chunk) */
     }
@@ -1122,7 +1376,18 @@ __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a)
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (a.mw_all) { /* no one-warp launch follows: the last CTA re-arms the counters for the next update */
+      __threadfence();
+      if (atomicAdd(&a.counters[2], 1) == (int)gridDim.x - 1) {
+        a.counters[0] = 0;
+        a.counters[1] = 0;
+        a.counters[2] = 0;
+        a.counters[3] = 0;
+      }
+    }
+  }
 }
 
 }  // namespace b200nav

@@ -47,3 +47,14 @@ for r in range(2):
     assert_layers_equal(cg.download("laser", robot=r), clay[r], "coded robot %d" % r)
 assert cg.layer_format("laser") == "coded"
 print("sanitize workload OK")
+
+# scan form (projection fused into the binning kernel, thinned scan with the ifClearEnd quirk) + asynchronous VFH+
+sg = DeviceGridMap(ctx, (12.8, 12.8), 0.05, n_robots=3, layers=("laser",))
+sg.alias("master", "laser")
+info = sg.scan_info(-2.3, 0.0043, 0.1, 6.0, 1080, decimate=True)
+for it in range(2):
+    poses = rng.uniform(-2, 2, (3, 3))
+    ranges = rng.uniform(0.05, 7.0, (3, 1080)).astype(np.float32)
+    ranges[rng.random(ranges.shape) < 0.1] = np.inf
+    sg.himm_update_scans_batched("laser", info, poses, ranges)
+print("sanitize scan-form workload OK")

@@ -411,6 +411,42 @@ def test_long_steady_state_fleet_sequence(ctx):
     dg.close()
 
 
+@pytest.mark.parametrize("n_robots,beams", [(1, 360), (1, 1080), (5, 720)])
+def test_uneven_beam_lengths_saturating_walls(ctx, n_robots, beams):
+    """Scans whose neighbouring beams differ wildly in length (a comb of near and far returns), replayed until the
+    walls saturate: consecutive 32-beam batches of a tile then cover very different step ranges, which is what the
+    multi-warp kernel's wavefront pipeline has to keep in order (a short batch must not let its successor overtake
+    an earlier, longer one)."""
+    rng = np.random.default_rng(beams + n_robots)
+    g = O.make_geom(10.0, 10.0, 0.05)
+    from ros_navigation_b200 import DeviceGridMap
+    dg = DeviceGridMap(ctx, (10.0, 10.0), 0.05, n_robots=n_robots, layers=("laser",))
+    layers = [O.new_layer(g) for _ in range(n_robots)]
+    centre = rng.uniform(-1.0, 1.0, (n_robots, 2))
+    comb = np.where(np.arange(beams) // rng.integers(3, 40) % 2 == 0, 0.35, 2.9)   # near / far teeth
+    for cycle in range(90):
+        per = []
+        for r in range(n_robots):
+            origin = centre[r] + 0.02 * cycle * np.array([np.cos(0.1 * cycle + r), np.sin(0.07 * cycle)])
+            th = -np.pi + 2 * np.pi * np.arange(beams) / beams
+            rad = comb * (1.0 + 0.02 * rng.standard_normal(beams))
+            if cycle % 9 == 4:
+                rad = np.roll(rad, int(rng.integers(1, 60)))
+            ex = (origin[0] + rad * np.cos(th)).astype(np.float32).astype(np.float64)
+            ey = (origin[1] + rad * np.sin(th)).astype(np.float32).astype(np.float64)
+            ce = (rng.random(beams) < 0.03).astype(np.int32)
+            per.append(O.make_samples(np.full(beams, origin[0]), np.full(beams, origin[1]), ex, ey, ce))
+        off = np.concatenate([[0], np.cumsum([len(p) for p in per])]).astype(np.int32)
+        dg.himm_update_batched("laser", np.concatenate(per), off)
+        for r in range(n_robots):
+            O.himm_update(g, layers[r], per[r])
+        if cycle % 15 == 14:
+            for r in range(n_robots):
+                assert_layers_equal(dg.download("laser", robot=r), layers[r], "cycle %d robot %d" % (cycle, r))
+    assert max(float(np.nanmax(l)) for l in layers) >= 170.0
+    dg.close()
+
+
 def test_c2_sized_grid_scan_sequence(ctx):
     """BASELINE config 2 geometry: 2048 x 2048 @ 5 cm, 1080-beam / 270 deg scans up to 30 m."""
     import torch

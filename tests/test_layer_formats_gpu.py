@@ -131,11 +131,14 @@ def test_float_layer_mode_runs_the_same_suites():
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
 
 
-def test_multi_warp_heavy_tile_kernel_runs_the_himm_suite():
-    """B200NAV_MW_HEAVY=1 hands the tile that holds a scan's origin to a CTA of four warps that split the rings of
-    the tile among them (himm_tile_coded_mw_kernel, experimental): same bits as the one-warp kernel."""
-    env = dict(os.environ, B200NAV_MW_HEAVY="1")
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_both_tile_kernels_run_the_himm_suite(mode):
+    """By default fleets of up to 32 robots are walked by himm_tile_coded_mw_kernel (CTAs of four warps share a tile
+    as a wavefront pipeline over the beam batches) and larger ones by the one-warp kernel.  B200NAV_MW_HEAVY=0 / =2
+    force one or the other for every fleet size: same bits either way."""
+    env = dict(os.environ, B200NAV_MW_HEAVY=mode)
     out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_himm_gpu.py", "-m", "gpu", "-x", "-q", "-k",
-                          "random or order or chunking or several or edge or batched or cloud_form_matches or long_steady",
-                          "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=400)
+                          "random or order or chunking or several or edge or batched or cloud_form_matches or long_steady "
+                          "or uneven or c2_sized",
+                          "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
