@@ -505,7 +505,10 @@ int himm_launch_prep(b200nav_grid* g, HimmArgs a, int beam_lo, int beam_hi, int 
   return check_launch(ctx, "himm_prep_kernel");
 }
 
-constexpr int kHeavyWarps = 4; /* warps per CTA of the multi-warp heavy-tile kernel */
+#ifndef B200NAV_HEAVY_WARPS
+#define B200NAV_HEAVY_WARPS 8 /* A/B on C2 / C3 (tile phase): 2 warps 47 / 137 us, 4: 33 / 82, 6: 32 / 69, 8: 30 / 61 */
+#endif
+constexpr int kHeavyWarps = B200NAV_HEAVY_WARPS; /* warps per CTA of the multi-warp tile kernel */
 constexpr int kMwAllRobots = 32; /* fleets up to this size: every tile item on a multi-warp CTA */
 
 int himm_launch_tile(b200nav_grid* g, const HimmArgs& a_in) {
@@ -513,7 +516,6 @@ int himm_launch_tile(b200nav_grid* g, const HimmArgs& a_in) {
   int jrc = join_side(ctx); /* a VFH+ update on the side stream may still read the layer this kernel rewrites */
   if (jrc) return jrc;
   HimmArgs a = a_in;
-  a.skip_heavy = 0;
   const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
   /* The tile that holds a scan's own origin sees every beam of the scan: walked by one warp it is the critical path
    * of a small update (a single robot: 0.057 of 0.095 ms per scan).  A fleet of up to kMwAllRobots robots cannot fill
@@ -527,7 +529,7 @@ int himm_launch_tile(b200nav_grid* g, const HimmArgs& a_in) {
   a.mw_all = (a.coded && (mw_mode == 2 || (mw_mode == 1 && a.n_active <= kMwAllRobots))) ? 1 : 0;
   if (a.mw_all) {
     ProfScope ps(ctx, PROF_HIMM_TILE_MW);
-    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * 8));
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)a.worklist_cap, (size_t)ctx->sm_count * (32 / kHeavyWarps)));
     himm_tile_coded_mw_kernel<kListCap, kHeavyWarps><<<blocks, 32 * kHeavyWarps, smem, ctx->stream>>>(a);
     return check_launch(ctx, "himm_tile_coded_mw_kernel");
   }

@@ -84,7 +84,6 @@ struct HimmArgs {
   int n_chunks;                   /* chunks per robot                             */
   int chunk_beams;                /* beams per chunk: multiple of 32, <= HIMM_CHUNK */
   int mask_words;                 /* chunk_beams / 32                              */
-  int skip_heavy;                 /* the one-warp tile kernel leaves the heavy items to himm_tile_coded_mw_kernel */
   int mw_all;                     /* small fleets: himm_tile_coded_mw_kernel takes EVERY item (no one-warp launch) */
 };
 
@@ -356,16 +355,10 @@ struct FloatView { /* global memory, in place (tiles with values outside the HIM
 
 /* Apply the listed beams, in order, to one tile through `view` (cell (r,c) of the tile lives at
  * view[(c-C0)*pitch + (r-R0)]).  32 list entries per batch; see the schedule description below. */
-/* NW > 1: the NW warps of a CTA work on ONE tile together.  Every warp holds the same 32 beams of a batch; the
- * rings of a fan batch are dealt round-robin in blocks of four steps (block = t >> 2, owner = block % NW).  A cell at
- * step t of a line from origin O has Chebyshev distance t from O, so for batches that share their origin a cell
- * always belongs to the same warp and that warp sees the batches in order: the per-cell order of the reference is
- * kept with no barrier between batches.  A change of origin or a non-fan batch makes all warps meet first. */
-template <class View, int NW = 1>
+template <class View>
 __device__ __forceinline__ void himm_apply_list(const View view, const int pitch, const BeamSeg* __restrict__ segs,
                                                 const uint16_t* list, const int n_list, const int R0, const int R1,
-                                                const int C0, const int C1, const int lane, const int warp = 0) {
-  int cur_origin = -1; /* NW > 1: origin cell shared by the fan batches since the last block barrier */
+                                                const int C0, const int C1, const int lane) {
   /* Lane-parallel set-up: lane L clips beam L of the batch to this tile and derives the Bresenham state at its
    * first step inside.  Then one of two exact schedules:
    *  (fan)     all beams of the batch start in the SAME cell (a lidar scan).  A cell at step t of such a line has
@@ -432,13 +425,6 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
        * them, so an iteration in which no lane sees a larger value and no lane marks needs no coordination at
        * all (the common case: free space).  Otherwise match.any groups the lanes by cell and the lowest lane of
        * each group applies the group's clears and +30 marks in lane order == sample order. ---- */
-      if (NW > 1) { /* batches of another origin may meet these cells at other steps: let every warp catch up */
-        const int origin = lr0 * 65536 + lc0;
-        if (cur_origin != origin) {
-          __syncthreads();
-          cur_origin = origin;
-        }
-      }
       const int first = (my_len > 0) ? my_t0 : 0x7fffffff;
       const unsigned span = (my_len > 0) ? (unsigned)(my_len - 1) : 0u;
       const int last = (my_len > 0) ? my_t0 + my_len - 1 : -0x7fffffff;
@@ -486,7 +472,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           }
         }
       };
-      if (NW == 1) {
+      {
         /* every lane starts at step tmin of ITS line and walks on from there */
         const int back = (my_len > 0) ? my_t0 - tmin : 0;
         const unsigned long long xs = dda_at(my_S, my_B, (unsigned)((my_len > 0) ? tmin : 0));
@@ -496,28 +482,10 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
         int k = (my_len > 0) ? tmin - first : -0x40000000;
         const int n_iter = (tmax - tmin) / RINGS;
         for (int i = 0; i <= n_iter; i++, k += RINGS) ring_block(k, off, frac);
-      } else {
-        /* my blocks of four absolute steps: block b = t >> 2 belongs to warp b % NW; the state at the block's first
-         * step comes from the closed form */
-        const int blk_lo = tmin >> 2, blk_hi = tmax >> 2;
-        int blk = blk_lo + ((warp - blk_lo) % NW + NW) % NW;
-        for (; blk <= blk_hi; blk += NW) {
-          const int tb = blk << 2;
-          const unsigned long long xs = dda_at(my_S, my_B, (unsigned)tb);
-          unsigned frac = (unsigned)xs;
-          const int q = my_diag ? 0 : (int)(xs >> 32);
-          int off = my_off0 + (tb - my_t0) * step_plain + (q - my_q0) * my_dn;
-          ring_block((my_len > 0) ? tb - first : -0x40000000, off, frac);
-        }
       }
       __syncwarp(); /* the next batch may read any cell this one wrote */
     } else {
       /* ---- general schedule ---- */
-      if (NW > 1) { /* one warp applies the batch while the others wait: any cell may be involved */
-        __syncthreads();
-        cur_origin = -1;
-        if (warp != 0) active = 0u;
-      }
       while (active) {
         const int src = __ffs(active) - 1;
         active &= active - 1;
@@ -556,7 +524,6 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           __syncwarp();
         }
       }
-      if (NW > 1) __syncthreads();
     }
   }
 }
@@ -881,7 +848,7 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
   const int n_tiles = a.tiles_r * a.tiles_c;
   const int n_heavy = *reinterpret_cast<volatile int*>(&a.counters[0]); /* final: the prep kernel has completed */
   const int n_light = *reinterpret_cast<volatile int*>(&a.counters[3]);
-  const int n_work = a.skip_heavy ? n_light : n_heavy + n_light;
+  const int n_work = n_heavy + n_light;
   if (lane == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -894,8 +861,7 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
     if (lane == 0) w = atomicAdd(&a.counters[1], 1);
     w = __shfl_sync(0xffffffffu, w, 0);
     if (w >= n_work) break;
-    const int rt = a.skip_heavy ? a.worklist[a.worklist_cap - 1 - w]
-                                : a.worklist[w < n_heavy ? w : a.worklist_cap - 1 - (w - n_heavy)];
+    const int rt = a.worklist[w < n_heavy ? w : a.worklist_cap - 1 - (w - n_heavy)];
     const int rel = rt / n_tiles, tile_id = rt - rel * n_tiles;
     const int robot = a.robot0 + rel;
     const int tile_r = tile_id % a.tiles_r, tile_c = tile_id / a.tiles_r;
@@ -1264,10 +1230,10 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
- * K1 for the "heavy" work items (the tile that holds a scan's own origin sees every beam of it) when there are few
- * robots: NW warps share one tile (see himm_apply_list<View, NW>), which cuts the latency of the longest item of a
- * single-robot update.  CTA b handles heavy items b, b + gridDim.x, ...; the one-warp kernel then only takes the
- * light items (HimmArgs::skip_heavy).
+ * K1 for small fleets (HimmArgs::mw_all: every touched tile; one warp per tile could not fill the GPU anyway, and the
+ * tile that holds a scan's own origin - it sees every beam - would keep a single warp busy for most of the update):
+ * NW warps share one tile as a wavefront pipeline over the beam batches (himm_apply_list_pipe).  CTA b handles work
+ * items b, b + gridDim.x, ... (the heavy origin tiles first); the last CTA re-arms the counters.
  * ------------------------------------------------------------------------------------------------------------- */
 template <int LIST_CAP, int NW>
 __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a) {
