@@ -368,7 +368,9 @@ class GpuArm:
         the tile / VFH+ kernels of cycle i.  The L2 flush runs in-stream between cycles (inside the caller's timed
         region)."""
         tickets = []
+        busy = 0.0   # host time spent enqueueing (everything except the waits for tickets)
         for k in range(n):
+            t_k = time.perf_counter()
             i = first + k
             c, slot = i % N_CYCLES, k & 1
             if flush:
@@ -380,6 +382,15 @@ class GpuArm:
                                                           self.h_offsets[c])
             if self.exchange is None:
                 self.vfh.update_batched_async(self.grid, "master", self.h_inputs[c], self.h_cmds[slot])
+            elif self.exchange.fleet is not None and not self.exchange.push:
+                # N > 1 without torch in the loop: inputs up, VFH+ kernel, NCCL all-gather and the copy of the whole
+                # fleet's table to pinned host memory are ONE enqueue-only library call on side streams
+                from ros_navigation_b200.capi import check, lib
+                if k >= 2:
+                    check(lib().b200nav_fleet_cycle_wait(self.exchange.fleet, slot), self.ctx.h)
+                check(lib().b200nav_fleet_cycle_async(self.exchange.fleet, self.vfh.h, self.grid.h, b"master",
+                                                      self.h_inputs[c].data_ptr(), slot, self.h_cmds[slot].data_ptr()),
+                      self.ctx.h)
             else:
                 self.d_inputs_e2e.copy_(self.h_inputs[c], non_blocking=True)
                 if self.exchange.push:
@@ -392,9 +403,15 @@ class GpuArm:
                 self.h_cmds[slot].copy_(self.exchange.tables[slot], non_blocking=True)
                 self.exchange.release(slot)  # peer push: the table has been read, peers may write the slot again
             tickets.append(self.ctx.fence())
+            busy += time.perf_counter() - t_k
             if k >= depth:
                 self.ctx.wait(tickets[k - depth])
+        self.e2e_enqueue_s = busy
         self.ctx.synchronize()
+        if self.exchange is not None and self.exchange.fleet is not None and not self.exchange.push:
+            from ros_navigation_b200.capi import check, lib
+            for slot in (0, 1):
+                check(lib().b200nav_fleet_cycle_wait(self.exchange.fleet, slot), self.ctx.h)
 
     def e2e_bytes(self, c):
         h2d = self.h_poses[c].numel() * 8 + self.h_ranges[c].numel() * 4 + self.h_inputs[c].numel()
@@ -528,6 +545,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         t0 = time.perf_counter()
         arm.run_e2e_pipelined(args.warmup, args.steps)
         e2e_s = time.perf_counter() - t0
+        e2e_enqueue_ms = getattr(arm, "e2e_enqueue_s", 0.0) * 1000.0 / max(args.steps, 1)
         clk = clocks.stop() if rank == 0 else None
 
     # first-pass number (all ranks take part): layers cleared to NaN, the first N_CYCLES cycles timed
@@ -597,6 +615,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                                "vfh_update": vfh_ms / max(vfh_n, 1)},
         "wall_s_timed_region": wall,
         "host_enqueue_ms_per_step": getattr(arm, "host_enqueue_ms_per_step", None),
+        "e2e_host_enqueue_ms_per_step": e2e_enqueue_ms, "cpu_affinity": args.cpu_affinity,
         "exchange_verified": (None if exchange_bad is None else
                               {"ranks": world, "mismatching_blocks": exchange_bad,
                                "how": "after the timed region: 2 more cycles, every rank checksums each rank's block of "
@@ -818,6 +837,26 @@ def batched_numbers(device, name, steps=12, warm=12, float_layers=False):
     return out
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Run this rank (and allocate its pinned buffers) on the CPUs of the NUMA node its GPU hangs off: with one
+    process per GPU the end-to-end feed otherwise crosses the socket interconnect for half of the GPUs."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        cpus = set()
+        for part in open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return "%d cpus of the GPU's NUMA node (%s)" % (len(cpus), bus)
+    except Exception as e:
+        return "unchanged (%s)" % type(e).__name__
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -840,6 +879,7 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
+    args.cpu_affinity = pin_to_gpu_numa_node(local_rank) if world > 1 else "unchanged (single rank)"
 
     import torch
     if not torch.cuda.is_available():

@@ -361,6 +361,15 @@ int b200nav_steer_update_goals(int n, const double* poses, const double* waypoin
                                int32_t* plan_index, float tolerance, const double* odom_speed,
                                b200nav_vfh_input* inputs, uint8_t* plan_done);
 
+/* One fleet cycle's steering step from pinned HOST buffers, enqueue only (the N > 1 form of
+ * b200nav_vfh_update_batched_async): inputs up, VFH+ kernel for this rank's robots, all-gather of the commands, the
+ * whole fleet's table (world x n_robots records, rank order) back into host_table - on side streams, overlapping the
+ * next cycle's copies and kernels.  Two slots; b200nav_fleet_cycle_wait(slot) blocks until host_table of the slot's
+ * last cycle is complete (call it before reusing the slot's host buffers).  NCCL exchange only. */
+int b200nav_fleet_cycle_async(b200nav_fleet* fleet, b200nav_vfh* vfh, b200nav_grid* grid, const char* layer,
+                              const b200nav_vfh_input* host_in, int slot, b200nav_command* host_table);
+int b200nav_fleet_cycle_wait(b200nav_fleet* fleet, int slot);
+
 /* Read back per-robot state after an update (any pointer may be NULL):
  *  origin_hist / hist / last_binary: hist_size floats (VFH::OriginHist, VFH::Hist, Last_Binary_Hist);
  *  scalars[4] = {Picked_Angle, Last_Picked_Angle, Desired_Angle, Blocked_Circle_Radius};

@@ -87,6 +87,9 @@ _SIGNATURES = {
     "b200nav_fleet_push_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200nav_fleet_table": (C.c_void_p, [C.c_void_p, C.c_int]),
     "b200nav_fleet_release": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200nav_fleet_cycle_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int,
+                                            C.c_void_p]),
+    "b200nav_fleet_cycle_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_steer_update_goals": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200nav_vfh_update_batched_dev_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]),

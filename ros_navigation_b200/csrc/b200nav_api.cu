@@ -176,6 +176,8 @@ struct b200nav_fleet {
   uint8_t* region = nullptr;
   size_t region_bytes = 0;
   uint8_t* peer_region[B200NAV_MAX_PEERS] = {nullptr};
+  DevBuf cyc_local[2], cyc_table[2]; /* b200nav_fleet_cycle_async: this rank's rows / the gathered table, per slot */
+  bool cyc_pending[2] = {false, false};
   unsigned long long epoch[2] = {0, 0};
   unsigned long long released[2] = {0, 0}; /* last epoch of the slot this rank has acknowledged as consumed */
   bool push_pending[2] = {false, false};
@@ -1489,6 +1491,10 @@ int b200nav_fleet_destroy(b200nav_fleet* f) {
     if (p != f->rank && f->peer_region[p]) cudaIpcCloseMemHandle(f->peer_region[p]);
   if (f->region) cudaFree(f->region);
   if (f->stream) cudaStreamSynchronize(f->stream);
+  for (int i = 0; i < 2; i++) {
+    f->cyc_local[i].release();
+    f->cyc_table[i].release();
+  }
   if (f->comm && f->CommDestroy) f->CommDestroy(f->comm);
   for (int i = 0; i < 2; i++) {
     if (f->ready[i]) cudaEventDestroy(f->ready[i]);
@@ -2095,6 +2101,81 @@ int b200nav_vfh_update_batched_dev(b200nav_vfh* v, b200nav_grid* g, const char* 
   CUDA_TRY(v->ctx, cudaSetDevice(v->ctx->device));
   { int jrc = join_side(v->ctx); if (jrc) return jrc; }
   return vfh_launch(v, g, l, dev_in, nullptr, dev_out, 0, v->n_robots);
+}
+
+/* One fleet cycle's steering step from HOST buffers, everything enqueued and nothing waited for: the inputs go up on
+ * the copy stream, the VFH+ kernel runs on the side stream behind this cycle's tile kernel and writes this rank's rows,
+ * the all-gather and the copy of the gathered table into pinned host memory run on the fleet's stream.  The next
+ * cycle's copies, binning and tile kernels overlap all of it (the next tile kernel only joins the side stream). */
+int b200nav_fleet_cycle_async(b200nav_fleet* f, b200nav_vfh* v, b200nav_grid* g, const char* layer,
+                              const b200nav_vfh_input* host_in, int slot, b200nav_command* host_table) {
+  if (!f || !v || !g || !host_in || !host_table || slot < 0 || slot > 1) return B200NAV_EINVAL;
+  b200nav_ctx* ctx = v->ctx;
+  if (f->ctx != ctx || g->ctx != ctx) return set_err(ctx, B200NAV_EINVAL, "fleet, grid and vfh belong to different contexts");
+  if (g->n_robots != v->n_robots) return set_err(ctx, B200NAV_EINVAL, "grid and vfh robot counts differ");
+  Layer* lay = find_layer(g, layer);
+  if (!lay) return set_err(ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  const int n = v->n_robots;
+  const size_t row_bytes = sizeof(b200nav_command) * (size_t)n;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctx->copy_events.resize(8);
+    for (auto& e : ctx->copy_events) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (!ctx->side_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_to_side, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_side_done, cudaEventDisableTiming));
+  }
+  if (f->cyc_local[slot].cap < row_bytes || f->cyc_table[slot].cap < row_bytes * (size_t)f->world) {
+    CUDA_TRY(ctx, sync_raw(ctx));
+    CUDA_TRY(ctx, cudaStreamSynchronize(f->stream));
+    CUDA_TRY(ctx, f->cyc_local[slot].reserve(row_bytes));
+    CUDA_TRY(ctx, f->cyc_table[slot].reserve(row_bytes * (size_t)f->world));
+  }
+  cudaStream_t run = ctx->side_stream;
+  /* inputs: double-buffered on the copy stream, as in the single-rank asynchronous update */
+  const int in_slot = v->in_slot;
+  v->in_slot ^= 1;
+  CUDA_TRY(ctx, v->in2[in_slot].reserve(sizeof(b200nav_vfh_input) * (size_t)n));
+  if (!v->in_ready) CUDA_TRY(ctx, cudaEventCreateWithFlags(&v->in_ready, cudaEventDisableTiming));
+  if (!v->in_done[in_slot]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&v->in_done[in_slot], cudaEventDisableTiming));
+  if (v->in_done_set[in_slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, v->in_done[in_slot], 0));
+  CUDA_TRY(ctx, cudaMemcpyAsync(v->in2[in_slot].p, host_in, sizeof(b200nav_vfh_input) * (size_t)n, cudaMemcpyHostToDevice,
+                                ctx->copy_stream));
+  CUDA_TRY(ctx, cudaEventRecord(v->in_ready, ctx->copy_stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_to_side, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev_to_side, 0));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(run, v->in_ready, 0));
+  /* the gather that last read this slot's rows (two cycles ago) must be done before they are rewritten */
+  if (f->cyc_pending[slot]) CUDA_TRY(ctx, cudaStreamWaitEvent(run, f->done[slot], 0));
+  int rc = vfh_launch(v, g, lay, static_cast<const b200nav_vfh_input*>(v->in2[in_slot].p), nullptr,
+                      static_cast<b200nav_command*>(f->cyc_local[slot].p), 0, n, run);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(v->in_done[in_slot], run));
+  v->in_done_set[in_slot] = true;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_side_done, run));
+  ctx->side_pending = true;
+  /* exchange + read-back on the fleet's stream */
+  CUDA_TRY(ctx, cudaEventRecord(f->ready[slot], run));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(f->stream, f->ready[slot], 0));
+  if (f->world > 1) {
+    const int r = f->AllGather(f->cyc_local[slot].p, f->cyc_table[slot].p, row_bytes, /*ncclUint8*/ 1, f->comm, f->stream);
+    if (r != 0) return set_err(ctx, B200NAV_ECUDA, "ncclAllGather: %s", f->ErrorString ? f->ErrorString(r) : "?");
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(host_table, f->world > 1 ? f->cyc_table[slot].p : f->cyc_local[slot].p,
+                                row_bytes * (size_t)f->world, cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(ctx, cudaEventRecord(f->done[slot], f->stream));
+  f->cyc_pending[slot] = true;
+  return B200NAV_OK;
+}
+
+/* Blocks the calling thread until the host table of the slot's last b200nav_fleet_cycle_async is complete. */
+int b200nav_fleet_cycle_wait(b200nav_fleet* f, int slot) {
+  if (!f || slot < 0 || slot > 1) return B200NAV_EINVAL;
+  if (f->cyc_pending[slot]) CUDA_TRY(f->ctx, cudaEventSynchronize(f->done[slot]));
+  return B200NAV_OK;
 }
 
 int b200nav_vfh_read_state(b200nav_vfh* v, int robot, float* origin_hist, float* hist, float* last_binary,

@@ -93,6 +93,36 @@ with torch.cuda.stream(stream):
         got = snap.cpu().numpy().view(capi.COMMAND_DTYPE).reshape(-1)["picked_angle"]
         assert np.all(got == np.float32(10.0 + cycle)), (rank, cycle, np.unique(got))
     push.status()
+    # b200nav_fleet_cycle_async: inputs from pinned host memory, VFH+ kernel, all-gather and the table back in pinned
+    # host memory, enqueue-only (what bench.py's end-to-end loop uses at N > 1) - against the explicit path
+    from ros_navigation_b200.capi import check, lib
+    vc, vd = VFH(ctx, n_robots=n_local), VFH(ctx, n_robots=n_local)
+    cyc = CommandExchange(n_local * world, dev, ctx=ctx)
+    h_tab = [torch.zeros(n_local * world, 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    wants, h_ins = [], []
+    for cycle in range(6):
+        slot = cycle & 1
+        inp = np.zeros(n_local, capi.VFH_INPUT_DTYPE)
+        inp["x"], inp["y"] = rng.uniform(-2, 2, n_local), rng.uniform(-2, 2, n_local)
+        inp["yaw"], inp["dt"], inp["current_speed"] = rng.uniform(-3, 3, n_local), 0.2, 50 * (cycle % 3)
+        inp["goal_direction"], inp["goal_distance"], inp["goal_tolerance"] = rng.uniform(0, 180, n_local), 2500.0, 250.0
+        h_in = torch.from_numpy(inp.view(np.uint8).reshape(n_local, -1)).pin_memory()
+        h_ins.append(h_in)
+        if cycle >= 2:
+            check(lib().b200nav_fleet_cycle_wait(cyc.fleet, slot), ctx.h)
+            assert torch.equal(h_tab[slot], wants[cycle - 2]), (rank, cycle - 2)
+        check(lib().b200nav_fleet_cycle_async(cyc.fleet, vc.h, grid.h, b"master", h_in.data_ptr(), slot,
+                                              h_tab[slot].data_ptr()), ctx.h)
+        plain.wait(slot)
+        vd.update_batched_dev(grid, "master", h_in.to(dev), plain.locals[slot])
+        plain.gather_async(slot)
+        plain.wait(slot)
+        stream.synchronize()
+        wants.append(plain.tables[slot].cpu().clone())
+    for cycle in (4, 5):
+        check(lib().b200nav_fleet_cycle_wait(cyc.fleet, cycle & 1), ctx.h)
+        assert torch.equal(h_tab[cycle & 1], wants[cycle]), (rank, cycle)
+    cyc.close()
     push.close(); plain.close()
 dist.barrier()
 dist.destroy_process_group()
