@@ -726,6 +726,7 @@ def sharded_numbers(torch, dist, device, name, rank, world, steps=12, warm=40):
     stream = torch.cuda.Stream(device)
     with torch.cuda.stream(stream):
         arm = GpuArm(name, lo, hi, device, stream, world, robots_total)
+        flush_l2(arm)   # allocates this context's flush scratch outside the timed loop (else the ranks skew)
         for w in range(warm):
             arm.step_dev(w, last=True)
         stream.synchronize()

@@ -104,7 +104,7 @@ with torch.cuda.stream(stream):
         slot = cycle & 1
         inp = np.zeros(n_local, capi.VFH_INPUT_DTYPE)
         inp["x"], inp["y"] = rng.uniform(-2, 2, n_local), rng.uniform(-2, 2, n_local)
-        inp["yaw"], inp["dt"], inp["current_speed"] = rng.uniform(-3, 3, n_local), 0.2, 50 * (cycle % 3)
+        inp["yaw"], inp["dt"], inp["current_speed"] = rng.uniform(-3, 3, n_local), 0.2, 50 * (cycle & 1)
         inp["goal_direction"], inp["goal_distance"], inp["goal_tolerance"] = rng.uniform(0, 180, n_local), 2500.0, 250.0
         h_in = torch.from_numpy(inp.view(np.uint8).reshape(n_local, -1)).pin_memory()
         h_ins.append(h_in)
