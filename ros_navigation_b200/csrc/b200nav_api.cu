@@ -397,6 +397,7 @@ int upload_geom(b200nav_grid* g) {
 }
 
 constexpr int kVfhMaxSmem = 200 * 1024;
+constexpr int kVfhManyWaves = 4096; /* robots per launch from which the occupancy-first VFH+ build is used */
 
 /* ---- HIMM launch ------------------------------------------------------------------------------------------- */
 constexpr int kSub = HIMM_TILE, kListCap = HIMM_CHUNK;
@@ -676,12 +677,12 @@ int vfh_launch(b200nav_vfh* v, b200nav_grid* g, const Layer* layer, const b200na
     if (ga.use_tma) tm = v->tmap;
     smem = vfh_smem_bytes(v, true, box_r, box_c);
     if (smem > (size_t)kVfhMaxSmem) return set_err(ctx, B200NAV_ERANGE, "VFH window too large for shared memory (%zu B)", smem);
-    auto kern = vfh_update_kernel<true>;
+    auto kern = n >= kVfhManyWaves ? vfh_update_kernel<true, 16> : vfh_update_kernel<true, 1>;
     ProfScope ps(ctx, PROF_VFH, stream);
     kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, nullptr, dev_out, robot0, push);
   } else {
     smem = vfh_smem_bytes(v, false, 0, 0);
-    auto kern = vfh_update_kernel<false>;
+    auto kern = n >= kVfhManyWaves ? vfh_update_kernel<false, 16> : vfh_update_kernel<false, 1>;
     ProfScope ps(ctx, PROF_VFH, stream);
     kern<<<n, B200NAV_VFH_THREADS, smem, stream>>>(v->dev, ga, tm, dev_in, dev_ranges, dev_out, robot0, push);
   }
@@ -696,8 +697,10 @@ int configure_kernels(b200nav_ctx* ctx) {
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
   CUDA_TRY(ctx, cudaFuncSetAttribute(himm_tile_coded_mw_kernel<kListCap, kHeavyWarps>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg::kSmemBytes));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(vfh_update_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVfhMaxSmem));
   return B200NAV_OK;
 }
 

@@ -91,10 +91,10 @@ struct HimmArgs {
  * K0: RangeSample -> BeamSeg, and binning: every tile the Bresenham line (or the mark) touches gets the beam's bit
  * in its beam mask (RED.OR).  Reading a mask in ascending bit order later yields the tile's beams in sample order
  * without any sort.
- * Warp-aggregated atomics: the 32 beams of a warp are consecutive samples, so neighbouring lanes mostly want to set
- * neighbouring bits of the SAME mask word.  The warp walks its beams' tile lists in lock step; a lane whose target
- * word equals its left neighbour's joins that neighbour's run, and the head of each run issues one RED.OR with the
- * run's (contiguous) bits.  ~10x fewer L2 reductions than one per (beam, tile).
+ * Warp-aggregated atomics: the 32 beams of a warp are consecutive samples = the 32 bits of ONE mask word per tile.
+ * The warp walks its beams' tile lists in lock step; match.any groups the lanes that emit the same tile in an
+ * iteration and the lowest lane of each group issues one RED.OR with the group's lane mask.  ~10x fewer L2
+ * reductions than one per (beam, tile).
  * ------------------------------------------------------------------------------------------------------------- */
 #ifndef HIMM_PREP_BLOCKS
 #define HIMM_PREP_BLOCKS 12
@@ -204,16 +204,14 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
     }
     if (__ballot_sync(0xffffffffu, have) == 0u) break;
     const int tile_id = tc * a.tiles_r + tr;
-    const long long widx = have ? (long long)((rc_base + (size_t)tile_id) * a.mask_words + word) : -1ll - lane;
-    /* runs of neighbouring lanes with the same target word: their bits are consecutive positions of that word */
-    const long long prev = __shfl_up_sync(0xffffffffu, widx, 1);
-    const int prev_bit = __shfl_up_sync(0xffffffffu, bitpos, 1);
-    const bool head = have && (lane == 0 || prev != widx || prev_bit + 1 != bitpos);
-    const unsigned breaks = __ballot_sync(0xffffffffu, head || !have);
+    /* All 32 beams of a warp share the mask word (a warp is 32 consecutive beams, bit = lane), so the lanes that
+     * emit the same tile in this iteration own exactly the bits of one word: match.any groups them and the lowest
+     * lane of each group issues ONE reduction with the group's lane mask. */
+    const unsigned group = __match_any_sync(0xffffffffu, have ? tile_id : -1 - lane);
+    const bool head = have && (group & ((1u << lane) - 1u)) == 0u;
     if (head) {
-      const unsigned rest = (lane == 31) ? 0u : (breaks >> (lane + 1));
-      const int run = rest ? __ffs(rest) : 32 - lane; /* lanes in my run */
-      const uint32_t bits = (run >= 32 ? 0xffffffffu : ((1u << run) - 1u)) << bitpos;
+      const size_t widx = (rc_base + (size_t)tile_id) * a.mask_words + word;
+      const uint32_t bits = group;
       atomicOr(&a.beam_masks[widx], bits);
       /* first touch of this (robot, tile) in this update: append it to the work list */
       const int rt = rel * n_tiles + tile_id;

@@ -192,8 +192,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
  * Fused kernel.  FROM_GRID: build the pseudo-scan from the grid window (stage R), else take dev_ranges.
  * Dynamic shared memory layout (bytes): ranges[361] double | nz[nf] u16 | hist[H] float | window floats (TMA).
  * -------------------------------------------------------------------------------------------------------------- */
-template <bool FROM_GRID>
-__global__ void __launch_bounds__(B200NAV_VFH_THREADS)
+/* MIN_BLOCKS: resident CTAs per SM the register allocation must allow.  1 (70 registers) is fastest while a launch
+ * is a single wave and the block's dependent chain sets the time (1024 robots: 23 vs 27 us); 16 (32 registers, a few
+ * spills) wins once there are many waves (16 384 robots: 213 vs 272 us).  The host picks by robot count. */
+template <bool FROM_GRID, int MIN_BLOCKS>
+__global__ void __launch_bounds__(B200NAV_VFH_THREADS, MIN_BLOCKS)
 vfh_update_kernel(const VfhDev v, const VfhGridArgs ga, const __grid_constant__ CUtensorMap tmap,
                   const b200nav_vfh_input* __restrict__ in, const double* __restrict__ dev_ranges,
                   b200nav_command* __restrict__ out, int robot0, const VfhPush push) {
