@@ -99,6 +99,7 @@ struct HimmArgs {
 #ifndef HIMM_PREP_BLOCKS
 #define HIMM_PREP_BLOCKS 12
 #endif
+#define HIMM_PREP_PROBE_WORDS 512 /* per-CTA "tile already probed" bits: grids of up to 16384 tiles */
 __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmArgs a) {
   /* grid = (blocks per robot, robots of this launch): the robot is the block's y index - no search through the
    * offsets - and a warp never straddles two robots */
@@ -112,6 +113,11 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
   }
   const int i = beg + blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0 && end - beg > a.n_chunks * a.chunk_beams) *a.error_flag = 1;
+  /* tiles this CTA has already probed for "first touch" (its 128 consecutive beams keep hitting the same tiles) */
+  __shared__ uint32_t s_probed[HIMM_PREP_PROBE_WORDS];
+  for (int w = threadIdx.x; w < min(HIMM_PREP_PROBE_WORDS, (a.tiles_r * a.tiles_c + 31) >> 5); w += blockDim.x)
+    s_probed[w] = 0u;
+  __syncthreads();
   if (beg + (int)(blockIdx.x * blockDim.x) + (threadIdx.x & ~31) >= end) return; /* whole warp beyond the robot's beams */
   const bool valid = i < end;
   BeamSeg b;
@@ -215,7 +221,13 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
       atomicOr(&a.beam_masks[widx], bits);
       /* first touch of this (robot, tile) in this update: append it to the work list */
       const int rt = rel * n_tiles + tile_id;
-      if (a.touched[rt] == 0u && atomicExch(&a.touched[rt], 1u) == 0u) {
+      /* the global first-touch flag is only consulted by the first group of this CTA that meets the tile */
+      bool probe = true;
+      if (n_tiles <= 32 * HIMM_PREP_PROBE_WORDS) {
+        const uint32_t bit = 1u << (tile_id & 31);
+        probe = (atomicOr(&s_probed[tile_id >> 5], bit) & bit) == 0u;
+      }
+      if (probe && a.touched[rt] == 0u && atomicExch(&a.touched[rt], 1u) == 0u) {
         /* The tile that holds the beams' own start cell sees every beam of the scan: such heavy items are queued
          * from the front of the list, all others from the back, so the long items start first (no long tail). */
         const bool heavy = b.r0 >= 0 && tr == b.r0 / HIMM_TILE && tc == b.c0 / HIMM_TILE;
