@@ -118,10 +118,12 @@ B200_HD double f64_div_by(double a, double b, double y) {
   return (fabs(r2) < fabs(r1)) ? qn : q1;
 }
 
-/* One Bresenham line in buffer-index space + the cell to mark. 24 bytes. */
-struct BeamSeg {
+/* One Bresenham line in buffer-index space + the cell to mark + the line's fixed-point DDA constants (dda_init:
+ * computed once per beam by the binning kernel instead of once per (beam, tile) by the tile kernel).  32 bytes. */
+struct __align__(16) BeamSeg {
   int r0, c0, r1, c1;   /* inclusive endpoints; r0 < 0: no line                    */
   int mr, mc;           /* cell that receives the +30 mark; mr < 0: no mark        */
+  unsigned S, B;        /* dda_init(add, den) of the line (0, 0 for 45-degree lines and when there is no line) */
 };
 
 B200_HD void wrap_index(int& index, int buffer_size) {
@@ -228,6 +230,7 @@ B200_HD BeamSeg make_beam(const GridDims& d, const RobotGeom& g, double sx, doub
   BeamSeg b;
   b.r0 = b.c0 = b.r1 = b.c1 = -1;
   b.mr = b.mc = -1;
+  b.S = b.B = 0u; /* filled in by the caller that needs them (himm_prep_kernel) */
   /* Non-finite coordinates would make the reference's clip loop spin forever; defined as "no line".  The mark
    * only depends on the end point (map_updater.h:44-49). */
   const bool finite = isfinite(sx) && isfinite(sy) && isfinite(ex) && isfinite(ey);

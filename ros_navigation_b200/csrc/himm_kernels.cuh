@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
   const bool valid = i < end;
   BeamSeg b;
   b.r0 = b.c0 = b.r1 = b.c1 = b.mr = b.mc = -1;
+  b.S = b.B = 0u;
   if (valid) {
     const RobotGeom g = a.geom[a.robot0 + rel];
     double sx, sy, ex, ey;
@@ -153,7 +154,6 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
       clear_end = a.clear_end ? a.clear_end[i] : 0;
     }
     b = make_beam(a.dims, g, sx, sy, ex, ey, clear_end);
-    a.segs[i] = b;
   }
 
   const int k = valid ? i - beg : 0; /* index of the beam within its robot */
@@ -171,7 +171,11 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
   /* per-lane iterator over the tiles of my beam: first the mark's tile, then band by band along the driving axis */
   const LineForm f = line_form(b);
   const unsigned den = (unsigned)max(f.den, 1);
-  const unsigned num0 = (unsigned)(f.den >> 1);
+  /* the line's fixed-point DDA constants: used below for the band ends (q(t) = high word of B + t S, exact) and
+   * handed to the tile kernel in the BeamSeg */
+  bool diag = false;
+  if (b.r0 >= 0) dda_init((unsigned)f.add, den, b.S, b.B, diag);
+  if (valid) a.segs[i] = b;
   const int band1 = (f.m0 + f.sm * f.den) / HIMM_TILE;
   int band = f.m0 / HIMM_TILE;
   bool mark_todo = binning && b.mr >= 0;
@@ -188,8 +192,8 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
         int tb = (f.sm > 0) ? (mhi - f.m0) : (f.m0 - mlo);
         ta = max(ta, 0);
         tb = min(tb, f.den);
-        const int qa = (int)((num0 + (unsigned)ta * (unsigned)f.add) / den);
-        const int qb = (int)((num0 + (unsigned)tb * (unsigned)f.add) / den);
+        const int qa = diag ? ta : (int)(dda_at(b.S, b.B, (unsigned)ta) >> 32); /* == (den/2 + ta * add) / den */
+        const int qb = diag ? tb : (int)(dda_at(b.S, b.B, (unsigned)tb) >> 32);
         const int na = f.n0 + f.sn * qa, nb = f.n0 + f.sn * qb; /* minor coordinate at both ends (monotone) */
         nt = min(na, nb) / HIMM_TILE;
         nt_hi = max(na, nb) / HIMM_TILE;
@@ -402,7 +406,9 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
         int t0, t1;
         if (clip_line_to_rect(f, R0, R1, C0, C1, t0, t1)) {
           const unsigned den = (unsigned)max(f.den, 1);
-          dda_init((unsigned)f.add, den, my_S, my_B, my_diag);
+          my_S = b.S; /* dda_init(add, den), computed once per beam by the binning kernel */
+          my_B = b.B;
+          my_diag = (unsigned)f.add >= den;
           const unsigned x0 = (unsigned)(f.den >> 1) + (unsigned)t0 * (unsigned)f.add;
           const unsigned q0 = my_diag ? (unsigned)t0 : (unsigned)(dda_at(my_S, my_B, (unsigned)t0) >> 32); /* == x0 / den */
           my_q0 = my_diag ? 0 : (int)q0;
@@ -1050,7 +1056,9 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
         int t0, t1;
         if (clip_line_to_rect(f, R0, R1, C0, C1, t0, t1)) {
           const unsigned den = (unsigned)max(f.den, 1);
-          dda_init((unsigned)f.add, den, my_S, my_B, my_diag);
+          my_S = b.S; /* dda_init(add, den), computed once per beam by the binning kernel */
+          my_B = b.B;
+          my_diag = (unsigned)f.add >= den;
           const unsigned x0 = (unsigned)(f.den >> 1) + (unsigned)t0 * (unsigned)f.add;
           const unsigned q0 = my_diag ? (unsigned)t0 : (unsigned)(dda_at(my_S, my_B, (unsigned)t0) >> 32);
           my_q0 = my_diag ? 0 : (int)q0;
