@@ -289,6 +289,46 @@ NAVH_API int navh_last_hist_msg(void* h, uint16_t* ydata36, uint16_t* ybin36) {
   return (int)m->num_bin;
 }
 
+#ifdef NAVH_DROPIN
+// The optional fast path of INTEGRATION.md section 3 (drop-in build only): Steerer::update's goal glue through
+// b200nav_steer_update_goals and VFH::Update_VFH_FromGrid on the device twin of MapProvider's map - no host submap
+// copy, no host atan2.  `plan` / `plan_index` play Steerer::plan_ / planIndex_.  Returns 0 when a command was computed.
+NAVH_API int navh_steer_from_grid(void* h, const double* plan_xy, int plan_n, int* plan_index, double odom_speed,
+                                  const char* layer, navh_steer_out* out) {
+  Nav* n = (Nav*)h;
+  standin::Scope scope(&n->world);
+  move_control::Steerer& s = *n->steerer;
+  grid_map::Position pos;
+  double yaw = 0;
+  if (!n->provider->getRobotPos(pos, yaw)) return -1;
+  const double pose[3] = {pos(0), pos(1), yaw};
+  const int32_t offs[2] = {0, plan_n};
+  b200nav_vfh_input in;
+  memset(&in, 0, sizeof(in));
+  uint8_t done = 0;
+  int32_t idx = *plan_index;
+  if (b200nav_steer_update_goals(1, pose, plan_xy, offs, &idx, 250.0f, &odom_speed, &in, &done) != B200NAV_OK) return -2;
+  *plan_index = idx;
+  memset(out, 0, sizeof(*out));
+  out->plan_ready = done ? 0 : 1;
+  if (done) return 1;
+  int speed = 0, turn = 0;
+  s.vfhP_->Update_VFH_FromGrid(n->provider->map_, layer, in.x, in.y, in.yaw, in.current_speed, in.goal_direction,
+                               in.goal_distance, in.goal_tolerance, speed, turn);
+  out->updated = 1;
+  out->linear_x = (float)(speed) / 1000.0;          /* Steerer::pubVel (steerer.cpp:193-199) */
+  out->angular_z = turn * M_PI / 180.0;
+  out->picked_angle = s.vfhP_->GetPickedAngle();
+  out->desired_angle = s.vfhP_->GetDesiredAngle();
+  const int hs = std::min(72, s.vfhP_->getHistSize());
+  for (int i = 0; i < hs; ++i) {
+    out->hist[i] = s.vfhP_->Hist[i];
+    out->origin_hist[i] = s.vfhP_->OriginHist[i];
+  }
+  return 0;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // Fleet cycle: the reference node of every robot fed one scan and asked for one decision, robots block-partitioned
 // over `threads` std::threads inside this one call (the CPU baseline of the batched configs).

@@ -58,6 +58,8 @@ def load(path):
     L.navh_last_hist_msg.argtypes = [vp, vp, vp]
     L.navh_fleet_cycle.argtypes = [vp, C.c_int, C.c_double, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float,
                                    C.c_float, vp, vp, vp, C.c_int]
+    if L.navh_is_dropin():
+        L.navh_steer_from_grid.argtypes = [vp, vp, C.c_int, ip, C.c_double, cp, C.POINTER(SteerOut)]
     if not L.navh_is_dropin():
         L.navh_fleet_cycle_samples.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp, vp, vp, C.c_int]
         L.navh_core_create.argtypes = [C.c_double] * 5 + [cp]
@@ -163,6 +165,19 @@ class Node:
                     ranges=np.frombuffer(o.ranges, dtype=np.float64).copy(),
                     hist=np.frombuffer(o.hist, dtype=np.float32).copy(),
                     origin_hist=np.frombuffer(o.origin_hist, dtype=np.float32).copy())
+
+    def steer_from_grid(self, plan, plan_index, odom_speed, layer="laser"):
+        """Drop-in build only: goal glue + VFH::Update_VFH_FromGrid on the device twin. Returns (rc, index, out)."""
+        plan = np.ascontiguousarray(plan, np.float64).reshape(-1, 2)
+        idx = C.c_int(int(plan_index))
+        o = SteerOut()
+        rc = self.L.navh_steer_from_grid(self.h, plan.ctypes.data, len(plan), C.byref(idx), float(odom_speed),
+                                         layer.encode(), C.byref(o))
+        return rc, idx.value, dict(linear_x=o.linear_x, angular_z=o.angular_z, updated=bool(o.updated),
+                                   plan_ready=bool(o.plan_ready), picked_angle=o.picked_angle,
+                                   desired_angle=o.desired_angle,
+                                   hist=np.frombuffer(o.hist, dtype=np.float32).copy(),
+                                   origin_hist=np.frombuffer(o.origin_hist, dtype=np.float32).copy())
 
     def hist_msg(self):
         a = np.zeros(36, np.uint16)

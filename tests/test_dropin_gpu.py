@@ -116,3 +116,41 @@ def test_dropin_moving_map_with_sonars_matches_reference():
     assert np.array_equal(ref.occupancy(), dut.occupancy())
     ref.close()
     dut.close()
+
+
+def test_dropin_fast_path_from_device_grid_matches_reference_steerer():
+    """INTEGRATION.md section 3: instead of Steerer::getRangesFromSubmap + Update_VFH on the host copy, the drop-in
+    VFH reads the window from the device twin of MapProvider's map (Update_VFH_FromGrid on layer "laser", which the
+    laser updater keeps current in HBM) with the goal computed by b200nav_steer_update_goals.  Commands, picked angle
+    and both histograms must equal what the reference's own Steerer::update publishes for the same scans and plan."""
+    extent, beams, fov, range_max = 10.0, 360, 2 * math.pi, 3.0
+    ref, dut = _both(extent, False)
+    world = synth.Worlds(1, extent, 2718)
+    amin, ainc = np.float32(-fov / 2), np.float32(fov / beams)
+    plan = np.array([[0.0, 0.0], [1.5, 1.0], [-2.0, 1.5], [0.5, -2.5]])
+    ref.accept_plan(plan)
+    idx, compared = 1, 0
+    for step in range(80):
+        t = 1.0 + 0.2 * (step + 1)
+        pose, ranges = _scan(world, t, beams, fov, range_max)
+        speed = 0.04 * (step % 6)
+        for n in (ref, dut):
+            n.set_time(t)
+            n.set_frame("base_link", *pose)
+            n.set_frame("laser", *pose)
+            n.publish_scan(ranges, float(amin), float(ainc), 0.1, range_max)
+            n.update_map()
+            n.publish_odom(speed)
+        want = ref.steer()
+        rc, idx, got = dut.steer_from_grid(plan, idx, speed, "laser")
+        assert rc in (0, 1)
+        assert got["plan_ready"] == want["plan_ready"], step
+        if not want["plan_ready"]:
+            break
+        for k in ("linear_x", "angular_z", "picked_angle", "desired_angle"):
+            assert got[k] == want[k], "%s differs at step %d: %r vs %r" % (k, step, got[k], want[k])
+        assert np.array_equal(got["origin_hist"], want["origin_hist"]) and np.array_equal(got["hist"], want["hist"]), step
+        compared += 1
+    assert compared >= 40
+    ref.close()
+    dut.close()
