@@ -833,6 +833,19 @@ def batched_numbers(device, name, steps=12, warm=12, float_layers=False):
            "tile_items_per_launch": {"walked": walked / steps, "dropped_known_free": skipped / steps},
            "roofline": {"kernel": "himm_tile_coded_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "avg_launch_ms": tile_ms / max(tile_n, 1)}}
+    # the VFH+ kernel against the issue peak where it is throughput bound (many waves): ncu instruction count of the
+    # same workload (profiles/issue.json) / this run's launch time
+    try:
+        vi = json.load(open(os.path.join(ROOT, "profiles", "issue.json"))).get(name + "_vfh")
+        mhz = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0)
+    except Exception:
+        vi, mhz = None, 1965.0
+    if vi and not float_layers:
+        ach = vi["warp_instructions_per_launch"] / (kms["vfh_update"] / 1e3)
+        out["vfh_roofline_issue"] = {"kernel": "vfh_update_kernel", "achieved": ach / 1e9, "peak": 148 * 4 * mhz * 1e6 / 1e9,
+                                     "unit": "G warp-instructions/s", "frac": ach / (148 * 4 * mhz * 1e6),
+                                     "decisions_per_launch": robots, "us_per_launch": kms["vfh_update"] * 1e3,
+                                     "source": vi.get("source")}
     del arm
     torch.cuda.empty_cache()
     return out
