@@ -423,6 +423,9 @@ class GpuArm:
         from ros_navigation_b200.capi import lib
         out = np.zeros(2, np.int64)
         lib().b200nav_himm_debug_tile_stats(self.grid.h, out.ctypes.data)
+        b = np.zeros(2, np.int64)
+        lib().b200nav_himm_debug_batch_stats(self.grid.h, b.ctypes.data)
+        self.last_batch_stats = (int(b[0]), int(b[1]))   # 32-beam batches set up / dropped as "only re-clears free blocks"
         return int(out[0]), int(out[1])
 
     def algorithmic_bytes(self, c):
@@ -519,6 +522,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         wall = time.perf_counter() - t_wall0
         launches = arm.ctx.launches - launches0
         tiles_skipped, tiles_processed = arm.tile_stats()
+        main_batches = arm.last_batch_stats
         tile_ms, tile_n, tile_parts = tile_phase(arm.ctx)
         prep_ms, prep_n = arm.ctx.profile_read("himm_prep")
         vfh_ms, vfh_n = arm.ctx.profile_read("vfh_update")
@@ -605,6 +609,12 @@ def run_gpu_arm(args, rank, world, local_rank):
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "avg_launch_ms": tile_avg_ms, "launches_timed": int(tile_n),
                      "visits_per_launch": float(np.mean([u[1] for u in used])),
+                     "beam_batches_per_launch": {"set_up": main_batches[0] / max(args.steps, 1),
+                                                 "dropped_only_free_blocks": main_batches[1] / max(args.steps, 1),
+                                                 "note": "a 32-beam batch of a tile whose segments all lie in 8x8-cell "
+                                                         "blocks known to be free (and not marked in this update) only "
+                                                         "re-clears free cells: it is dropped before the walk; its visits "
+                                                         "still count in algorithmic_bytes"},
                      "tile_items_per_launch": {"walked": tiles_processed / max(args.steps, 1),
                                                "dropped_known_free": tiles_skipped / max(args.steps, 1),
                                                "note": "steady state (free space already 0): a touched tile whose cells are "
@@ -714,6 +724,8 @@ def cold_grid_numbers(torch, stream, arm, robots_total, alg, hbm_peak):
             "steps": N_CYCLES, "himm_tile_ms": tile_avg,
             "roofline_frac": alg_bytes / (tile_avg / 1e3) / 1e9 / hbm_peak,
             "tile_items_per_launch": {"walked": walked / N_CYCLES, "dropped_known_free": skipped / N_CYCLES},
+            "beam_batches_per_launch": {"set_up": arm.last_batch_stats[0] / N_CYCLES,
+                                        "dropped_only_free_blocks": arm.last_batch_stats[1] / N_CYCLES},
             "how": "layer cleared to NaN, cycles 0..%d timed with CUDA events, L2 flushed before each" % (N_CYCLES - 1)}
 
 

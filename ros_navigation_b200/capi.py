@@ -120,6 +120,7 @@ _SIGNATURES = {
 _DEBUG_SIGNATURES = {
     "b200nav_vfh_debug_disable_tma": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_himm_debug_tile_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200nav_himm_debug_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -2256,6 +2256,21 @@ int b200nav_himm_debug_tile_stats(b200nav_grid* g, int64_t* out2) {
   return B200NAV_OK;
 }
 
+/* Statistics hook: out[0] = 32-beam batches the tile kernel set up, out[1] = batches it dropped before the walk because
+ * all their segments only re-clear known-free blocks (FreeBlocks, himm_kernels.cuh), since the last call. */
+int b200nav_himm_debug_batch_stats(b200nav_grid* g, int64_t* out2) {
+  if (!g || !out2) return B200NAV_EINVAL;
+  out2[0] = out2[1] = 0;
+  if (!g->counters.p) return B200NAV_OK;
+  int c[8];
+  CUDA_TRY(g->ctx, sync_raw(g->ctx));
+  CUDA_TRY(g->ctx, cudaMemcpy(c, g->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+  out2[0] = c[6];
+  out2[1] = c[7];
+  CUDA_TRY(g->ctx, cudaMemset(static_cast<int*>(g->counters.p) + 6, 0, 2 * sizeof(int)));
+  return B200NAV_OK;
+}
+
 /* Test hook (not part of the drop-in surface): force the coalesced-load window path instead of TMA. */
 #ifdef VFH_STAGE_CLOCKS
 int b200nav_vfh_debug_stage_clocks(unsigned long long* out8, int reset) {

@@ -120,7 +120,7 @@ B200_HD double f64_div_by(double a, double b, double y) {
 
 /* One Bresenham line in buffer-index space + the cell to mark + the line's fixed-point DDA constants (dda_init:
  * computed once per beam by the binning kernel instead of once per (beam, tile) by the tile kernel).  32 bytes. */
-struct __align__(16) BeamSeg {
+struct alignas(16) BeamSeg {
   int r0, c0, r1, c1;   /* inclusive endpoints; r0 < 0: no line                    */
   int mr, mc;           /* cell that receives the +30 mark; mr < 0: no mark        */
   unsigned S, B;        /* dda_init(add, den) of the line (0, 0 for 45-degree lines and when there is no line) */

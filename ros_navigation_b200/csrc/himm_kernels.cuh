@@ -369,10 +369,23 @@ struct FloatView { /* global memory, in place (tiles with values outside the HIM
 
 /* Apply the listed beams, in order, to one tile through `view` (cell (r,c) of the tile lives at
  * view[(c-C0)*pitch + (r-R0)]).  32 list entries per batch; see the schedule description below. */
+/* What is known about a tile before its beams are applied: which of its 8 x 8 blocks of 8 x 8 cells hold nothing but
+ * free cells (value 0; bit bc * 8 + br, block column bc, block row br; the per-tile summary the tile kernel keeps in
+ * HimmArgs::free_cols), minus the blocks a mark of an earlier beam of this update has landed in.  A beam segment whose
+ * end cells' block box lies in such blocks, and that does not mark in this tile, only re-clears free cells (a
+ * Bresenham line is monotone, so all its cells lie in that box): it is dropped before the walk.  Exact: clearing a
+ * free cell leaves it free, and only a mark can make a free cell non-free during an update. */
+struct FreeBlocks {
+  uint32_t lo, hi;             /* summary as loaded for this work item (block columns 0..3 / 4..7) */
+  uint32_t dirty_lo, dirty_hi; /* blocks marked by the batches applied so far (this one included) */
+  int batches, dropped;        /* statistics: 32-beam batches seen / dropped entirely */
+};
+
 template <class View>
 __device__ __forceinline__ void himm_apply_list(const View view, const int pitch, const BeamSeg* __restrict__ segs,
                                                 const uint16_t* list, const int n_list, const int R0, const int R1,
-                                                const int C0, const int C1, const int lane) {
+                                                const int C0, const int C1, const int lane,
+                                                FreeBlocks* fb = nullptr) {
   /* Lane-parallel set-up: lane L clips beam L of the batch to this tile and derives the Bresenham state at its
    * first step inside.  Then one of two exact schedules:
    *  (fan)     all beams of the batch start in the SAME cell (a lidar scan).  A cell at step t of such a line has
@@ -398,8 +411,21 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
     unsigned my_S = 0u, my_B = 0u; /* fixed-point slope / half offset (dda_init) */
     bool my_diag = false;
     bool mark_at_end = false; /* the mark cell is the last cell of my segment */
+    const bool has_mark = have && b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1;
+    uint32_t eff_lo = 0u, eff_hi = 0u; /* blocks that are free and stay free while this batch is applied */
+    if (fb) { /* warp-uniform */
+      uint32_t mk_lo = 0u, mk_hi = 0u;
+      if (has_mark) {
+        const int bit = ((b.mc - C0) >> 3) * 8 + ((b.mr - R0) >> 3);
+        if (bit < 32) mk_lo = 1u << bit;
+        else mk_hi = 1u << (bit - 32);
+      }
+      fb->dirty_lo |= __reduce_or_sync(0xffffffffu, mk_lo);
+      fb->dirty_hi |= __reduce_or_sync(0xffffffffu, mk_hi);
+      eff_lo = fb->lo & ~fb->dirty_lo;
+      eff_hi = fb->hi & ~fb->dirty_hi;
+    }
     if (have) {
-      const bool has_mark = b.mr >= R0 && b.mr <= R1 && b.mc >= C0 && b.mc <= C1;
       if (has_mark) my_moff = view.bias() + (b.mc - C0) * pitch + (b.mr - R0);
       if (b.r0 >= 0) {
         const LineForm f = line_form(b);
@@ -425,11 +451,28 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           my_r0 = b.r0;
           my_c0 = b.c0;
           mark_at_end = has_mark && t1 == f.den && b.r1 == b.mr && b.c1 == b.mc;
+          if (!has_mark && (eff_lo | eff_hi) != 0u) {
+            /* block box of the segment's two end cells against the known-free blocks (see FreeBlocks) */
+            const unsigned q1 = my_diag ? (unsigned)t1 : (unsigned)(dda_at(my_S, my_B, (unsigned)t1) >> 32);
+            const int mj1 = f.m0 + f.sm * t1, mn1 = f.n0 + f.sn * (int)q1;
+            const int re = f.row_major ? mj1 : mn1, ce = f.row_major ? mn1 : mj1;
+            const int bra = (min(r, re) - R0) >> 3, brb = (max(r, re) - R0) >> 3;
+            const int bca = (min(c, ce) - C0) >> 3, bcb = (max(c, ce) - C0) >> 3;
+            const uint32_t rep = (((2u << (brb - bra)) - 1u) << bra) * 0x01010101u; /* the block rows, in every byte */
+            uint32_t need_lo = 0u, need_hi = 0u;
+            if (bca <= 3) need_lo = rep & (0xffffffffu >> (8 * (3 - min(bcb, 3)))) & (0xffffffffu << (8 * bca));
+            if (bcb >= 4) need_hi = rep & (0xffffffffu >> (8 * (7 - bcb))) & (0xffffffffu << (8 * (max(bca, 4) - 4)));
+            if (((need_lo & ~eff_lo) | (need_hi & ~eff_hi)) == 0u) my_len = 0; /* only re-clears free cells */
+          }
         }
       }
     }
     const bool has_work = my_len > 0 || my_moff >= 0;
     unsigned active = __ballot_sync(0xffffffffu, has_work);
+    if (fb) {
+      fb->batches++;
+      if (active == 0u) fb->dropped++;
+    }
     if (active == 0u) continue;
     /* fan test: every lane with work has a segment, marks sit on segment ends, one common start cell */
     const int lead = __ffs(active) - 1;
@@ -888,7 +931,13 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
     else beg = __ldg(&a.offsets[rel]);
     uint8_t* grec = static_cast<uint8_t*>(a.layer) + ((size_t)robot * n_tiles + tile_id) * HIMM_TILE_BYTES;
     if (lane == 0) a.touched[rt] = 0u;
-    const bool known_free = a.free_cols[rt] == ~0ull; /* warp-uniform load */
+    const unsigned long long fsum = a.free_cols[rt]; /* warp-uniform load: known-free 8 x 8 blocks of the tile */
+    const bool known_free = fsum == ~0ull;
+    FreeBlocks fb;
+    fb.lo = (uint32_t)fsum;
+    fb.hi = (uint32_t)(fsum >> 32);
+    fb.dirty_lo = fb.dirty_hi = 0u;
+    fb.batches = fb.dropped = 0;
     bool staged = false; /* copy-in issued */
     bool ready = false;  /* copy-in complete (waited for) */
 
@@ -954,7 +1003,7 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
         phase ^= 1u;
         ready = true;
       }
-      himm_apply_list(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane);
+      himm_apply_list(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane, &fb);
       __syncwarp(); /* the list is rewritten by the next chunk */
     }
 
@@ -963,22 +1012,39 @@ __global__ void __launch_bounds__(32, 30) himm_tile_coded_kernel(HimmArgs a) {
         mbar_wait(mbar, phase);
         phase ^= 1u;
       }
-      /* is the whole record free now?  (pad bytes and cells outside the grid hold the free code for good) */
-      unsigned diff = 0;
-      for (int i = lane; i < HIMM_TILE_BYTES / 16; i += 32) {
-        uint32_t x, y, z, q;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(q) : "r"(tile_saddr + 16 * i) : "memory");
-        diff |= (x ^ 0x01010101u) | (y ^ 0x01010101u) | (z ^ 0x01010101u) | (q ^ 0x01010101u);
+      /* Which 8 x 8 blocks of the record hold nothing but free cells now?  (cells outside the grid hold the free code
+       * for good.)  Lane L owns columns 2L and 2L+1: eight block-row bits per column from sixteen words, ANDed over
+       * the eight columns (four lanes) of a block column, gathered into the 64-bit summary (bit bc * 8 + br). */
+      uint32_t m = 0xffu;
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        const uint32_t col = tile_saddr + (uint32_t)((2 * lane + cc) * HIMM_TILE_PITCH);
+#pragma unroll
+        for (int br = 0; br < 8; br++) {
+          uint32_t w0, w1;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(col + 8 * br) : "memory");
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(col + 8 * br + 4) : "memory");
+          if (((w0 ^ 0x01010101u) | (w1 ^ 0x01010101u)) != 0u) m &= ~(1u << br);
+        }
       }
-      const bool all_free = !__any_sync(0xffffffffu, diff != 0u);
+      m &= __shfl_xor_sync(0xffffffffu, m, 1);
+      m &= __shfl_xor_sync(0xffffffffu, m, 2);
+      const int bc = lane >> 2;
+      const uint32_t sum_lo = __reduce_or_sync(0xffffffffu, ((lane & 3) == 0 && bc < 4) ? m << (8 * bc) : 0u);
+      const uint32_t sum_hi = __reduce_or_sync(0xffffffffu, ((lane & 3) == 0 && bc >= 4) ? m << (8 * (bc - 4)) : 0u);
+      const unsigned long long new_sum = ((unsigned long long)sum_hi << 32) | sum_lo;
       /* generic-proxy writes of the walk -> visible to the async proxy, then one lane sends the record home */
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grec), "r"(tile_saddr), "n"(HIMM_TILE_BYTES) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (all_free != known_free) a.free_cols[rt] = all_free ? ~0ull : 0ull;
+        if (new_sum != fsum) a.free_cols[rt] = new_sum;
       }
+    }
+    if (lane == 0 && fb.batches) { /* statistics: 32-beam batches seen / dropped because they only re-clear free cells */
+      atomicAdd(&a.counters[6], fb.batches);
+      if (fb.dropped) atomicAdd(&a.counters[7], fb.dropped);
     }
     __syncwarp();
   } /* persistent loop */
