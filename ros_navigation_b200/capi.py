@@ -121,6 +121,7 @@ _DEBUG_SIGNATURES = {
     "b200nav_vfh_debug_disable_tma": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_himm_debug_tile_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200nav_himm_debug_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200nav_himm_debug_free_summary": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int]),
 }
 
 _lib = None

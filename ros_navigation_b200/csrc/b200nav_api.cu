@@ -2256,6 +2256,22 @@ int b200nav_himm_debug_tile_stats(b200nav_grid* g, int64_t* out2) {
   return B200NAV_OK;
 }
 
+/* Test hook (not part of the drop-in surface): the tile kernel's per-tile summaries of one robot's layer - 64 bits per
+ * 64 x 64 tile, bit bc * 8 + br set = the 8 x 8 cells of block column bc / block row br are all known free (value 0).
+ * out = tiles_r * tiles_c words (tile index = tile_col * tiles_r + tile_row); all zero for FLOAT layers. */
+int b200nav_himm_debug_free_summary(b200nav_grid* g, const char* layer, int robot, uint64_t* out, int cap) {
+  if (!g || !out || robot < 0 || robot >= g->n_robots) return B200NAV_EINVAL;
+  Layer* l = find_layer(g, layer);
+  if (!l) return set_err(g->ctx, B200NAV_ENOLAYER, "no layer '%s'", layer ? layer : "(null)");
+  const int nt = (int)grid_tiles(g);
+  if (cap < nt) return B200NAV_EINVAL;
+  memset(out, 0, sizeof(uint64_t) * (size_t)nt);
+  if (!l->free_cols) return nt;
+  CUDA_TRY(g->ctx, sync_raw(g->ctx));
+  CUDA_TRY(g->ctx, cudaMemcpy(out, l->free_cols + (size_t)nt * robot, sizeof(uint64_t) * (size_t)nt, cudaMemcpyDeviceToHost));
+  return nt;
+}
+
 /* Statistics hook: out[0] = 32-beam batches the tile kernel set up, out[1] = batches it dropped before the walk because
  * all their segments only re-clear known-free blocks (FreeBlocks, himm_kernels.cuh), since the last call. */
 int b200nav_himm_debug_batch_stats(b200nav_grid* g, int64_t* out2) {

@@ -524,3 +524,52 @@ def test_c4_full_size_properties(ctx):
         vals = np.unique(lay[~np.isnan(lay)])
         assert set(vals).issubset(set(np.arange(0, 190, 10.0))), (r, vals)
     dg.close()
+
+
+def test_free_block_summaries_never_claim_a_non_free_block(ctx):
+    """The tile kernel drops beam batches that only re-clear blocks its per-tile summary calls free.  The summary must
+    therefore never claim a block that holds anything but 0.0 - checked against the downloaded layer after a long
+    sequence with moves, uploads and clears in between (every other writer of the layer must reset it)."""
+    from ros_navigation_b200 import DeviceGridMap, synth
+    from ros_navigation_b200.capi import lib
+    n, beams, rmax = 40, 1080, 6.0     # > 32 robots: the one-warp kernel (the one that keeps block summaries)
+    W = synth.Worlds(n, 12.8, seed=99)
+    dg = DeviceGridMap(ctx, (12.8, 12.8), 0.05, n_robots=n, layers=("laser",))
+    nt = ((dg.rows + 63) // 64) * ((dg.cols + 63) // 64)
+    tiles_r = (dg.rows + 63) // 64
+
+    def check(tag):
+        claimed = 0
+        for robot in (0, 7, n - 1):
+            lay = dg.download("laser", robot=robot)            # [col][row]
+            out = np.zeros(nt, np.uint64)
+            assert lib().b200nav_himm_debug_free_summary(dg.h, b"laser", robot, out.ctypes.data, nt) == nt
+            for t in range(nt):
+                tc, tr = t // tiles_r, t % tiles_r
+                w64 = int(out[t])
+                for bit in range(64):
+                    if (w64 >> bit) & 1:
+                        bc, br = bit // 8, bit % 8
+                        blk = lay[tc * 64 + bc * 8:tc * 64 + bc * 8 + 8, tr * 64 + br * 8:tr * 64 + br * 8 + 8]
+                        assert blk.size == 0 or np.all(blk == 0.0), (tag, robot, t, bc, br)
+                        claimed += 1
+        return claimed
+
+    total = 0
+    for c in range(40):
+        x, y, yaw = W.pose(0.2 * c)
+        r, ang = W.cast(x, y, yaw, beams, 1.5 * np.pi, rmax)
+        org, xy, clr, off = synth.cloud_from_scan(x, y, yaw, r, ang, rmax)
+        dg.himm_update_cloud_batched("laser", org.numpy(), xy.numpy(), clr.numpy(), off.numpy())
+        if c == 15:
+            dg.move((0.4, -0.3), robot=7)
+        if c == 22:
+            lay = dg.download("laser", robot=0)
+            lay[100:140, 90:130] = 50.0
+            dg.upload("laser", lay, robot=0)
+        if c == 30:
+            dg.clear("laser")
+        if c % 8 == 7:
+            total += check("cycle %d" % c)
+    assert total > 100, "the summaries never recorded a free block"
+    dg.close()
