@@ -2266,7 +2266,7 @@ int b200nav_himm_debug_free_summary(b200nav_grid* g, const char* layer, int robo
   const int nt = (int)grid_tiles(g);
   if (cap < nt) return B200NAV_EINVAL;
   memset(out, 0, sizeof(uint64_t) * (size_t)nt);
-  if (!l->free_cols) return nt;
+  if (!l->free_cols || !l->coded) return nt; /* FLOAT layers keep per-column summaries in the same words */
   CUDA_TRY(g->ctx, sync_raw(g->ctx));
   CUDA_TRY(g->ctx, cudaMemcpy(out, l->free_cols + (size_t)nt * robot, sizeof(uint64_t) * (size_t)nt, cudaMemcpyDeviceToHost));
   return nt;

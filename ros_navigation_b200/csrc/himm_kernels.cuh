@@ -68,9 +68,11 @@ struct HimmArgs {
   int* worklist;
   int worklist_cap;               /* entries in worklist[] (n_active * n_tiles)                              */
   int* counters;
-  /* free_cols[robot*n_tiles + tile]: bit c set => every cell of column c of that tile holds exactly 0 (free).
-   * Maintained by the tile kernel at write-back, reset by every other writer of the layer.  A tile whose beams
-   * only cross free columns and carry no mark cannot change (clearing 0 gives 0) and is skipped outright. */
+  /* free_cols[robot*n_tiles + tile]: 64 bits of "known to hold exactly 0 (free)" per 64 x 64 tile.  FLOAT layers: bit c
+   * = column c of the tile; CODED layers: bit bc * 8 + br = the 8 x 8 cells of block column bc / block row br
+   * (FreeBlocks below).  All ones = the whole tile is free in both.  Maintained by the tile kernel at write-back,
+   * reset by every other writer of the layer and whenever the layer changes its format.  Beams that only re-clear
+   * known-free cells and carry no mark cannot change anything (clearing 0 gives 0) and are skipped. */
   unsigned long long* free_cols;
   int robot0;                     /* first robot handled by blockIdx.y == 0       */
   int n_active;                   /* robots handled by this launch                */
