@@ -556,21 +556,37 @@ def test_free_block_summaries_never_claim_a_non_free_block(ctx):
         return claimed
 
     total = 0
+    spots = (0, 7, n - 1)     # the same robots are also followed by the oracle: batches dropped as "only re-clears
+    geoms = {r: O.make_geom(12.8, 12.8, 0.05) for r in spots}   # free blocks" must not change a single cell
+    layers = {r: O.new_layer(geoms[r]) for r in spots}
     for c in range(40):
         x, y, yaw = W.pose(0.2 * c)
         r, ang = W.cast(x, y, yaw, beams, 1.5 * np.pi, rmax)
         org, xy, clr, off = synth.cloud_from_scan(x, y, yaw, r, ang, rmax)
         dg.himm_update_cloud_batched("laser", org.numpy(), xy.numpy(), clr.numpy(), off.numpy())
+        offs = off.numpy()
+        for k in spots:
+            sl = slice(offs[k], offs[k + 1])
+            cnt = offs[k + 1] - offs[k]
+            O.himm_update(geoms[k], layers[k], O.make_samples(np.full(cnt, float(x[k])), np.full(cnt, float(y[k])),
+                                                              xy[sl, 0].double().numpy(), xy[sl, 1].double().numpy(),
+                                                              clr[sl].numpy()))
         if c == 15:
             dg.move((0.4, -0.3), robot=7)
+            O.move(geoms[7], [layers[7]], 0.4, -0.3)
         if c == 22:
             lay = dg.download("laser", robot=0)
             lay[100:140, 90:130] = 50.0
             dg.upload("laser", lay, robot=0)
+            layers[0][100:140, 90:130] = 50.0
         if c == 30:
             dg.clear("laser")
+            for k in spots:
+                layers[k][...] = np.nan
         if c % 8 == 7:
             total += check("cycle %d" % c)
+            for k in spots:
+                assert_layers_equal(dg.download("laser", robot=k), layers[k], "cycle %d robot %d" % (c, k))
     if dg.layer_format("laser") == "coded":   # FLOAT layers only ever record whole tiles
         assert total > 100, "the summaries never recorded a free block"
     dg.close()
