@@ -62,6 +62,7 @@ struct b200nav_ctx {
   size_t flush_cap = 0;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_to_side = nullptr, ev_side_done = nullptr;
+  cudaEvent_t ev_side_kernel = nullptr;    /* the side stream's last VFH+ KERNEL is done (its copy-out may still run) */
   bool side_pending = false;
   ProfSlot prof[PROF_KINDS];
   char err[512] = {0};
@@ -242,6 +243,13 @@ int join_side(b200nav_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side_done, 0));
     ctx->side_pending = false;
   }
+  return B200NAV_OK;
+}
+
+/* The tile kernel only has to wait for the side stream's VFH+ kernel (the reader of the layer it rewrites), not for
+ * the copy of the commands to the host that follows it there; side_pending stays set for everybody else. */
+int join_side_layer_writer(b200nav_ctx* ctx) {
+  if (ctx->side_pending) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_side_kernel ? ctx->ev_side_kernel : ctx->ev_side_done, 0));
   return B200NAV_OK;
 }
 
@@ -516,7 +524,7 @@ constexpr int kMwAllRobots = 32; /* fleets up to this size: every tile item on a
 
 int himm_launch_tile(b200nav_grid* g, const HimmArgs& a_in) {
   b200nav_ctx* ctx = g->ctx;
-  int jrc = join_side(ctx); /* a VFH+ update on the side stream may still read the layer this kernel rewrites */
+  int jrc = join_side_layer_writer(ctx); /* a VFH+ update on the side stream may still read the layer this kernel rewrites */
   if (jrc) return jrc;
   HimmArgs a = a_in;
   const size_t smem = TileCfg::kTileBytes + sizeof(uint16_t) * (size_t)a.chunk_beams;
@@ -782,6 +790,7 @@ int b200nav_ctx_destroy(b200nav_ctx* ctx) {
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->ev_to_side) cudaEventDestroy(ctx->ev_to_side);
   if (ctx->ev_side_done) cudaEventDestroy(ctx->ev_side_done);
+  if (ctx->ev_side_kernel) cudaEventDestroy(ctx->ev_side_kernel);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -2066,6 +2075,10 @@ static int vfh_run_host(b200nav_vfh* v, b200nav_grid* g, const char* layer, int 
     CUDA_TRY(ctx, cudaEventRecord(v->in_done[slot], run));
     v->in_done_set[slot] = true;
   }
+  if (run != ctx->stream) { /* the layer's reader is done here; the copy-out below need not hold the next tile kernel */
+    if (!ctx->ev_side_kernel) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_side_kernel, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_side_kernel, run));
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(host_out, v->out_buf.p, sizeof(b200nav_command) * (size_t)n, cudaMemcpyDeviceToHost, run));
   if (run != ctx->stream) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_side_done, run));
@@ -2163,6 +2176,8 @@ int b200nav_fleet_cycle_async(b200nav_fleet* f, b200nav_vfh* v, b200nav_grid* g,
   if (rc) return rc;
   CUDA_TRY(ctx, cudaEventRecord(v->in_done[in_slot], run));
   v->in_done_set[in_slot] = true;
+  if (!ctx->ev_side_kernel) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_side_kernel, cudaEventDisableTiming));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_side_kernel, run));
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_side_done, run));
   ctx->side_pending = true;
   /* exchange + read-back on the fleet's stream */
