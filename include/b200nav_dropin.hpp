@@ -72,6 +72,10 @@ class DeviceMap {
    * updater maintains through update() are already current; any other layer (e.g. "master", which MapProvider
    * composes on the host) is uploaded on every call. */
   bool make_readable(const std::string& layer) { return make_current(layer, false); }
+  /* Forget what is known about the device copy of `layer` (the next update uploads the host matrix first).  Called
+   * when an updater finds its layer missing on the host: a GridMap that was just (re)created - possibly at the address
+   * of an earlier one - must not inherit that one's device state. */
+  void invalidate(const std::string& layer) { epoch_of_.erase(layer); }
   /* device -> host matrix */
   bool pull(const std::string& layer) {
     grid_map::Matrix& m = host_[layer];

@@ -25,8 +25,10 @@ class MapUpdater {
 public:
     MapUpdater(ros::NodeHandle& nh, tf::TransformListener& tf, grid_map::GridMap &map, const std::string& typeName):
         typeName_(typeName), nh_(nh), tf_(tf), map_(map), device_(b200nav::device_map_for(map)) {
-        if (!map_.exists(typeName))
+        if (!map_.exists(typeName)) {
             map_.add(typeName);
+            device_.invalidate(typeName);   // a fresh host layer: whatever the device twin held under this name is stale
+        }
     }
     virtual ~MapUpdater() {}
     // update map and point out the map range updated
