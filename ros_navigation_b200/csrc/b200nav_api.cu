@@ -575,6 +575,12 @@ int himm_check_error_flag(b200nav_grid* g) {
   if (!g->errflag.p) return B200NAV_OK;
   int flag = 0;
   CUDA_TRY(g->ctx, cudaMemcpy(&flag, g->errflag.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag == 2) {
+    cudaMemset(g->errflag.p, 0, sizeof(int));
+    return set_err(g->ctx, B200NAV_ECUDA,
+                   "the multi-warp tile kernel gave up waiting for a predecessor batch (internal error): the layer of "
+                   "this update is not valid");
+  }
   if (flag) {
     cudaMemset(g->errflag.p, 0, sizeof(int));
     return set_err(g->ctx, B200NAV_ERANGE,

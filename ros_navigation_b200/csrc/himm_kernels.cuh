@@ -1096,7 +1096,16 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
                                                      const BeamSeg* __restrict__ segs, const uint16_t* list,
                                                      const int n_list, const int R0, const int R1, const int C0,
                                                      const int C1, const int lane, const int warp,
-                                                     const uint32_t prog /* shared address of NW progress words */) {
+                                                     const uint32_t prog /* shared address of NW progress words */,
+                                                     int* err) {
+  /* Every wait below is for a warp of the same CTA that makes progress on its own (independent thread scheduling);
+   * the bound only exists so that a logic error could never wedge the GPU: it raises the update's error flag. */
+  unsigned spins = 0u;
+  auto stuck = [&]() {
+    if (++spins < (1u << 27)) return false;
+    *err = 2;
+    return true;
+  };
   constexpr int RINGS = 4;
   const uint32_t my_word = prog + 8u * (uint32_t)warp, pred_word = prog + 8u * (uint32_t)((warp + NW - 1) % NW);
   BeamSeg nb;
@@ -1165,8 +1174,9 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
       unsigned long long p;
       do {
         p = pipe_load(pred_word);
-      } while ((p >> 48) < (unsigned long long)jb ||
-               ((p >> 48) == (unsigned long long)jb && ((p >> 32) & 0xffffull) != HIMM_PIPE_DONE));
+      } while (((p >> 48) < (unsigned long long)jb ||
+                ((p >> 48) == (unsigned long long)jb && ((p >> 32) & 0xffffull) != HIMM_PIPE_DONE)) &&
+               !stuck());
     };
     /* announce the batch (nothing done yet) */
     if (lane == 0) pipe_store(my_word, tag | origin);
@@ -1182,13 +1192,13 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
       unsigned long long p;
       do {
         p = pipe_load(pred_word);
-      } while ((p >> 48) < (unsigned long long)jb); /* batch jb - 1 not announced yet */
+      } while ((p >> 48) < (unsigned long long)jb && !stuck()); /* batch jb - 1 not announced yet */
       if ((p >> 48) > (unsigned long long)jb || ((p >> 32) & 0xffffull) == HIMM_PIPE_DONE) {
         pred_done = true;
       } else if (!fan || (p & 0xffffffffull) != origin) {
         do { /* other origin, or one of us is no fan: any cell may be shared at any step */
           p = pipe_load(pred_word);
-        } while ((p >> 48) == (unsigned long long)jb && ((p >> 32) & 0xffffull) != HIMM_PIPE_DONE);
+        } while ((p >> 48) == (unsigned long long)jb && ((p >> 32) & 0xffffull) != HIMM_PIPE_DONE && !stuck());
         pred_done = true;
       } else {
         pred_steps = (unsigned)((p >> 32) & 0xffffull);
@@ -1220,7 +1230,7 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
               break;
             }
             pred_steps = (unsigned)((p >> 32) & 0xffffull);
-            if (pred_steps >= need) break;
+            if (pred_steps >= need || stuck()) break;
           }
           __threadfence_block();
         }
@@ -1405,7 +1415,8 @@ __global__ void __launch_bounds__(32 * NW) himm_tile_coded_mw_kernel(HimmArgs a)
         }
         if (threadIdx.x == 0) atomicAdd(&a.counters[5], 1); /* statistics: tiles processed */
         const BeamSeg* segs = a.segs + beg + chunk * a.chunk_beams;
-        himm_apply_list_pipe<NW>(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane, warp, prog);
+        himm_apply_list_pipe<NW>(CodeView{tile_saddr}, HIMM_TILE_PITCH, segs, list, n_list, R0, R1, C0, C1, lane, warp, prog,
+                                 a.error_flag);
       }
       __syncthreads(); /* all warps are done with the list (and with the tile, after the last chunk) */
     }
