@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
     const int tile_id = tc * a.tiles_r + tr;
     /* All 32 beams of a warp share the mask word (a warp is 32 consecutive beams, bit = lane), so the lanes that
      * emit the same tile in this iteration own exactly the bits of one word: match.any groups them and the lowest
-     * lane of each group issues ONE reduction with the group's lane mask. */
-    const unsigned group = __match_any_sync(0xffffffffu, have ? tile_id : -1 - lane);
+     * lane of each group issues ONE reduction with the group's lane mask.  Idle lanes share one key (match.any
+     * costs issue time per distinct key). */
+    const unsigned group = __match_any_sync(0xffffffffu, have ? tile_id : -1);
     const bool head = have && (group & ((1u << lane) - 1u)) == 0u;
     if (head) {
       const size_t widx = (rc_base + (size_t)tile_id) * a.mask_words + word;
@@ -304,9 +305,10 @@ struct HimmTileCfg {
 };
 
 /* Tile views: the walk is written once against this interface.
- *   sensitive(off)   does the result of visiting this cell depend on how many beams visit it / in which order?
- *                    (code <= 1, i.e. NaN or 0: any number of clears gives 0 -> not sensitive)
- *   set_free(off)    result of >= 1 clears on a non-sensitive cell
+ *   peek(off)        the cell as stored; >= 2 means the result of visiting it depends on how many beams visit it and
+ *                    in which order (code <= 1, i.e. NaN or 0: any number of clears gives 0)
+ *   set_free(off)    result of >= 1 clears on a cell that is not sensitive in that sense
+ *   clear_n_known / clear_seq_known   the same on a cell whose content the caller read in this ring block
  *   clear_n / clear_seq   exact application of a group of visits */
 /* Shared-memory byte access through an explicit 32-bit shared address (a generic pointer would cost an address
  * space conversion on every access of the hot loop). */
@@ -322,8 +324,19 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, int v) {
 struct CodeView { /* shared memory, one byte per cell; offsets are shared-space byte addresses (bias()) */
   uint32_t base; /* shared-space address of the tile */
   __device__ __forceinline__ int bias() const { return (int)base; }
-  __device__ __forceinline__ bool sensitive(int off) const { return lds_u8(off) >= 2; }
+  __device__ __forceinline__ int peek(int off) const { return lds_u8(off); }
   __device__ __forceinline__ void set_free(int off) const { sts_u8(off, 1); }
+  /* clear_n / clear_seq on a cell whose content `c` the caller has already read (and nobody wrote since) */
+  __device__ __forceinline__ void clear_n_known(int off, int c, int n) const { sts_u8(off, max(c - n, 1)); }
+  __device__ __forceinline__ void clear_seq_known(int off, int c, unsigned group, unsigned marks) const {
+    while (group) {
+      const unsigned bit = group & (0u - group);
+      group ^= bit;
+      c = max(c - 1, 1);
+      if (marks & bit) c = (c <= 16) ? c + 3 : c;
+    }
+    sts_u8(off, c);
+  }
   __device__ __forceinline__ void clear_n(int off, int n, bool mark) const {
     int c = max(lds_u8(off) - n, 1);
     if (mark) c = (c <= 16) ? c + 3 : c;
@@ -348,8 +361,12 @@ struct CodeView { /* shared memory, one byte per cell; offsets are shared-space 
 struct FloatView { /* global memory, in place (tiles with values outside the HIMM set) */
   volatile float* p;
   __device__ __forceinline__ int bias() const { return 0; }
-  __device__ __forceinline__ bool sensitive(int) const { return true; }
+  __device__ __forceinline__ int peek(int) const { return 2; }
   __device__ __forceinline__ void set_free(int off) const { p[off] = 0.0f; }
+  __device__ __forceinline__ void clear_n_known(int off, int, int n) const { clear_n(off, n, false); }
+  __device__ __forceinline__ void clear_seq_known(int off, int, unsigned group, unsigned marks) const {
+    clear_seq(off, group, marks);
+  }
   __device__ __forceinline__ void clear_n(int off, int n, bool mark) const {
     float v = p[off];
     for (int i = 0; i < n; i++) v = himm_clear(v);
@@ -499,14 +516,14 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
       constexpr int RINGS = 4;
       auto ring_block = [&](const int k, int& off, unsigned& frac) {
         int offs[RINGS];
-        bool hot[RINGS]; /* my cell of ring r holds a value that counts visits (code >= 2) */
+        int val[RINGS]; /* my cell of ring r as read (a value >= 2 counts visits); 0 when I am not on the ring */
         bool sens = mark_k >= 0 && (unsigned)(mark_k - k) < (unsigned)RINGS; /* I mark inside this block */
 #pragma unroll
         for (int r = 0; r < RINGS; r++) {
           offs[r] = off;
           const bool on = (unsigned)(k + r) <= span;
-          hot[r] = on && view.sensitive(off);
-          sens = sens || hot[r];
+          val[r] = on ? view.peek(off) : 0;
+          sens = sens || val[r] >= 2;
           const unsigned nf = frac + my_S;
           off += (nf < frac) ? step_carry : step_plain;
           frac = nf;
@@ -517,15 +534,17 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
           for (int r = 0; r < RINGS; r++)
             if ((unsigned)(k + r) <= span) view.set_free(offs[r]);
         } else {
+          /* match.any costs issue time in proportion to the number of DISTINCT keys in the warp (measured on B200:
+           * ~4 cycles for one key, 31-83 for 32): lanes that are not on the ring share one key. */
 #pragma unroll
           for (int r = 0; r < RINGS; r++) {
             const bool on = (unsigned)(k + r) <= span, marking = k + r == mark_k;
-            if (__any_sync(0xffffffffu, hot[r] || (on && marking))) {
-              const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1 - lane);
+            if (__any_sync(0xffffffffu, val[r] >= 2 || (on && marking))) {
+              const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1);
               const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
               if (on && (group & ((1u << lane) - 1u)) == 0u) {
-                if (marks == 0u) view.clear_n(offs[r], __popc(group), false);
-                else view.clear_seq(offs[r], group, marks);
+                if (marks == 0u) view.clear_n_known(offs[r], val[r], __popc(group));
+                else view.clear_seq_known(offs[r], val[r], group, marks);
               }
             } else if (on) {
               view.set_free(offs[r]);
@@ -1241,14 +1260,14 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
         }
         /* one block of RINGS steps: identical to himm_apply_list's ring_block */
         int offs[RINGS];
-        bool hot[RINGS];
+        int val[RINGS];
         bool sens = mark_k >= 0 && (unsigned)(mark_k - k) < (unsigned)RINGS;
 #pragma unroll
         for (int r = 0; r < RINGS; r++) {
           offs[r] = off;
           const bool on = (unsigned)(k + r) <= span;
-          hot[r] = on && view.sensitive(off);
-          sens = sens || hot[r];
+          val[r] = on ? view.peek(off) : 0;
+          sens = sens || val[r] >= 2;
           const unsigned nf = frac + my_S;
           off += (nf < frac) ? step_carry : step_plain;
           frac = nf;
@@ -1262,12 +1281,12 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
 #pragma unroll
           for (int r = 0; r < RINGS; r++) {
             const bool on = (unsigned)(k + r) <= span, marking = k + r == mark_k;
-            if (__any_sync(0xffffffffu, hot[r] || (on && marking))) {
-              const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1 - lane);
+            if (__any_sync(0xffffffffu, val[r] >= 2 || (on && marking))) {
+              const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1);
               const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
               if (on && (group & ((1u << lane) - 1u)) == 0u) {
-                if (marks == 0u) view.clear_n(offs[r], __popc(group), false);
-                else view.clear_seq(offs[r], group, marks);
+                if (marks == 0u) view.clear_n_known(offs[r], val[r], __popc(group));
+                else view.clear_seq_known(offs[r], val[r], group, marks);
               }
             } else if (on) {
               view.set_free(offs[r]);
