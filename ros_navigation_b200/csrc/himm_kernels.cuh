@@ -940,7 +940,9 @@ __global__ void __launch_bounds__(32, B200NAV_TILE_MIN_BLOCKS) himm_tile_coded_k
   }
   __syncwarp();
   uint32_t phase = 0; /* mbarrier phase parity of the next copy-in */
-  /* work items are claimed one ahead: the atomic's round trip hides behind the current item */
+  /* Work items are claimed when the warp is free, never ahead: a pre-claimed item waits for its owner while other
+   * warps idle, and items differ in length by two orders of magnitude (measured at C4: claiming one ahead 0.153 ->
+   * 0.213 ms; one ahead only behind light items 0.163 ms). */
   for (;;) {
     int w = 0;
     if (lane == 0) w = atomicAdd(&a.counters[1], 1);
