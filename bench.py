@@ -436,14 +436,17 @@ class GpuArm:
 
 
 def tile_phase(ctx):
-    """Device time of the tile walk of an update = the multi-warp kernel for the heavy (origin) tiles plus the
-    one-warp kernel for the rest, back to back on one stream.  Returns (summed ms, number of updates, parts)."""
+    """Device time of the tile walk of an update: the one-warp-per-tile kernel (fleets) or the multi-warp kernel
+    (fleets of up to 32 robots: every tile on an 8-warp CTA); an update launches exactly one of them.
+    Returns (summed ms, number of updates, parts)."""
     one_ms, one_n = ctx.profile_read("himm_tile")
     mw_ms, mw_n = ctx.profile_read("himm_tile_mw")
-    parts = {"himm_tile_coded_kernel": one_ms / max(one_n, 1)}
+    parts = {}
+    if one_n:
+        parts["himm_tile_coded_kernel"] = one_ms / one_n
     if mw_n:
         parts["himm_tile_coded_mw_kernel"] = mw_ms / mw_n
-    return one_ms + mw_ms, one_n, parts
+    return one_ms + mw_ms, max(one_n, mw_n), parts
 
 
 def flush_l2_light(arm):
