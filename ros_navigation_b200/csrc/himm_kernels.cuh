@@ -1108,13 +1108,17 @@ __global__ void __launch_bounds__(32, B200NAV_TILE_MIN_BLOCKS) himm_tile_coded_k
 #define HIMM_PIPE_DONE 0xffffull
 #define HIMM_PIPE_NOFAN 0xffffffffull
 
+/* The progress words are the ONLY synchronisation between the warps of a CTA inside a list: a release store after the
+ * warp's cell writes (ordered before it by __syncwarp), an acquire load before the successor's cell reads.
+ * compute-sanitizer's racecheck does not model synchronisation through memory and reports these words and the cells
+ * they guard as hazards (profiles/README.md); the one-warp kernel is racecheck-clean. */
 __device__ __forceinline__ unsigned long long pipe_load(uint32_t addr) {
   unsigned long long v;
-  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ void pipe_store(uint32_t addr, unsigned long long v) {
-  asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+  asm volatile("st.release.cta.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
 template <int NW>

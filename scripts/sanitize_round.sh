@@ -1,15 +1,22 @@
 #!/bin/bash
-# compute-sanitizer evidence for the final build (run under gpurun): memcheck, racecheck and synccheck over
-# scripts/sanitize.py (float layers, byte-coded layers, scan form), plus racecheck with the multi-warp heavy-tile
-# kernel.  Summaries land in gpurun_out/sanitizer_<tool>[_mw].log; copy them to profiles/.
+# compute-sanitizer evidence for the final build (run under gpurun) over scripts/sanitize.py (float layers, byte-coded
+# layers, scan form; fleets of 2-3 robots):
+#   memcheck, synccheck          default kernels (small fleets: the multi-warp pipeline tile kernel)
+#   racecheck                    one warp per tile (B200NAV_MW_HEAVY=0): must report 0 hazards
+#   racecheck_mw                 the multi-warp pipeline kernel: its warps synchronise through release / acquire progress
+#                                words in shared memory, which racecheck does not model - it reports those words and
+#                                the cells they guard (expected; every report must be pipe_load / pipe_store / lds_u8 /
+#                                sts_u8 inside himm_apply_list_pipe)
+# Summaries land in gpurun_out/sanitizer_<tool>_<tag>.log; copy them to profiles/.
 TAG=${1:-r2}
 mkdir -p gpurun_out
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize.py > gpurun_out/sanitizer_${tool}_${TAG}.full 2>&1
-  echo "exit code $?" >> gpurun_out/sanitizer_${tool}_${TAG}.full
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize .*OK|exit code|Error|error|hazard" gpurun_out/sanitizer_${tool}_${TAG}.full | head -40 > gpurun_out/sanitizer_${tool}_${TAG}.log
-done
-B200NAV_MW_HEAVY=1 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/sanitize.py > gpurun_out/sanitizer_racecheck_mw_${TAG}.full 2>&1
-echo "exit code $?" >> gpurun_out/sanitizer_racecheck_mw_${TAG}.full
-grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize .*OK|exit code|Error|error|hazard" gpurun_out/sanitizer_racecheck_mw_${TAG}.full | head -40 > gpurun_out/sanitizer_racecheck_mw_${TAG}.log
-tail -n 4 gpurun_out/sanitizer_*_${TAG}.log
+run() { # name, tool, env
+  env $3 timeout 900 compute-sanitizer --tool $2 --print-limit 20 python scripts/sanitize.py > gpurun_out/sanitizer_$1_${TAG}.full 2>&1
+  echo "exit code $?" >> gpurun_out/sanitizer_$1_${TAG}.full
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize .*OK|exit code|Error|error" gpurun_out/sanitizer_$1_${TAG}.full | sed -E 's/\+0x[0-9a-f]+//' | sort | uniq -c | sort -rn | head -30 > gpurun_out/sanitizer_$1_${TAG}.log
+}
+run memcheck memcheck B200NAV_MW_HEAVY=1
+run synccheck synccheck B200NAV_MW_HEAVY=1
+run racecheck racecheck B200NAV_MW_HEAVY=0
+run racecheck_mw racecheck B200NAV_MW_HEAVY=1
+tail -n 8 gpurun_out/sanitizer_*_${TAG}.log
