@@ -493,6 +493,8 @@ int himm_setup(b200nav_grid* g, Layer* lay, const b200nav_sample* dev_samples, c
   a.worklist = static_cast<int*>(g->worklist.p);
   a.counters = static_cast<int*>(g->counters.p);
   a.worklist_cap = (int)n_robot_tiles;
+  a.mw_all = 0;
+  a.defer_first_touch = n_active < kVfhManyWaves ? 1 : 0; /* see himm_prep_kernel; same threshold as the VFH+ builds */
   g->last_total = total;
   return B200NAV_OK;
 }

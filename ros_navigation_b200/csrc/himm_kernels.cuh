@@ -87,6 +87,7 @@ struct HimmArgs {
   int chunk_beams;                /* beams per chunk: multiple of 32, <= HIMM_CHUNK */
   int mask_words;                 /* chunk_beams / 32                              */
   int mw_all;                     /* small fleets: himm_tile_coded_mw_kernel takes EVERY item (no one-warp launch) */
+  int defer_first_touch;          /* prep kernel: first-touch probes after the binning loop (small / medium fleets) */
 };
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -98,6 +99,14 @@ struct HimmArgs {
  * iteration and the lowest lane of each group issues one RED.OR with the group's lane mask.  ~10x fewer L2
  * reductions than one per (beam, tile).
  * ------------------------------------------------------------------------------------------------------------- */
+/* First touch of (robot, tile) `rt` in this update: append it to the work list (heavy items from the front). */
+__device__ __forceinline__ void himm_first_touch(const HimmArgs& a, int rt, bool heavy) {
+  if (a.touched[rt] == 0u && atomicExch(&a.touched[rt], 1u) == 0u) {
+    if (heavy) a.worklist[atomicAdd(&a.counters[0], 1)] = rt;
+    else a.worklist[a.worklist_cap - 1 - atomicAdd(&a.counters[3], 1)] = rt;
+  }
+}
+
 #ifndef HIMM_PREP_BLOCKS
 #define HIMM_PREP_BLOCKS 12
 #endif
@@ -115,13 +124,23 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
   }
   const int i = beg + blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0 && end - beg > a.n_chunks * a.chunk_beams) *a.error_flag = 1;
-  /* tiles this CTA has already probed for "first touch" (its 128 consecutive beams keep hitting the same tiles) */
-  __shared__ uint32_t s_probed[HIMM_PREP_PROBE_WORDS];
-  for (int w = threadIdx.x; w < min(HIMM_PREP_PROBE_WORDS, (a.tiles_r * a.tiles_c + 31) >> 5); w += blockDim.x)
+  /* Tiles this CTA's 128 consecutive beams touch (they keep hitting the same ones) and which of them hold a beam's own
+   * start cell.  The global first-touch probe and the work-list append are done once per CTA and tile AFTER the beams
+   * are binned, one lane per tile (HimmArgs::defer_first_touch): inside the loop each probe is a dependent global
+   * round trip that stalls its whole warp (10 % of the kernel's stall samples at C4: 0.052 -> 0.047 ms).  A launch
+   * that fills the GPU many times over hides that latency anyway and probes at once (C5: 0.430 against 0.455 ms). */
+  __shared__ uint32_t s_probed[HIMM_PREP_PROBE_WORDS], s_heavy[HIMM_PREP_PROBE_WORDS];
+  const int probe_words = min(HIMM_PREP_PROBE_WORDS, (a.tiles_r * a.tiles_c + 31) >> 5);
+  const bool fits = a.tiles_r * a.tiles_c <= 32 * HIMM_PREP_PROBE_WORDS; /* the bitmap covers the robot's tiles */
+  const bool deferred = fits && a.defer_first_touch != 0;
+  for (int w = threadIdx.x; w < probe_words; w += blockDim.x) {
     s_probed[w] = 0u;
+    s_heavy[w] = 0u;
+  }
   __syncthreads();
-  if (beg + (int)(blockIdx.x * blockDim.x) + (threadIdx.x & ~31) >= end) return; /* whole warp beyond the robot's beams */
-  const bool valid = i < end;
+  /* a warp wholly beyond the robot's beams bins nothing (it still joins the barrier below) */
+  const bool warp_live = beg + (int)(blockIdx.x * blockDim.x) + (threadIdx.x & ~31) < end;
+  const bool valid = warp_live && i < end;
   BeamSeg b;
   b.r0 = b.c0 = b.r1 = b.c1 = b.mr = b.mc = -1;
   b.S = b.B = 0u;
@@ -184,7 +203,7 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
   bool line_todo = binning && b.r0 >= 0;
   int nt = 0, nt_hi = -1; /* tiles nt..nt_hi of the current band still to emit */
 
-  for (;;) {
+  while (warp_live) {
     int tr = 0, tc = 0;
     bool have = false;
     if (line_todo) {
@@ -226,21 +245,35 @@ __global__ void __launch_bounds__(128, HIMM_PREP_BLOCKS) himm_prep_kernel(HimmAr
       const size_t widx = (rc_base + (size_t)tile_id) * a.mask_words + word;
       const uint32_t bits = group;
       atomicOr(&a.beam_masks[widx], bits);
-      /* first touch of this (robot, tile) in this update: append it to the work list */
-      const int rt = rel * n_tiles + tile_id;
-      /* the global first-touch flag is only consulted by the first group of this CTA that meets the tile */
-      bool probe = true;
-      if (n_tiles <= 32 * HIMM_PREP_PROBE_WORDS) {
+      /* The tile that holds the beams' own start cell sees every beam of the scan: such heavy items are queued
+       * from the front of the work list, all others from the back, so the long items start first (no long tail). */
+      const bool heavy = b.r0 >= 0 && tr == b.r0 / HIMM_TILE && tc == b.c0 / HIMM_TILE;
+      if (deferred) {
         const uint32_t bit = 1u << (tile_id & 31);
-        probe = (atomicOr(&s_probed[tile_id >> 5], bit) & bit) == 0u;
+        atomicOr(&s_probed[tile_id >> 5], bit);
+        if (heavy) atomicOr(&s_heavy[tile_id >> 5], bit);
+      } else { /* probe at once, but only the first group of this CTA that meets the tile */
+        bool probe = true;
+        if (fits) {
+          const uint32_t bit = 1u << (tile_id & 31);
+          probe = (atomicOr(&s_probed[tile_id >> 5], bit) & bit) == 0u;
+        }
+        if (probe) himm_first_touch(a, rel * n_tiles + tile_id, heavy);
       }
-      if (probe && a.touched[rt] == 0u && atomicExch(&a.touched[rt], 1u) == 0u) {
-        /* The tile that holds the beams' own start cell sees every beam of the scan: such heavy items are queued
-         * from the front of the list, all others from the back, so the long items start first (no long tail). */
-        const bool heavy = b.r0 >= 0 && tr == b.r0 / HIMM_TILE && tc == b.c0 / HIMM_TILE;
-        if (heavy) a.worklist[atomicAdd(&a.counters[0], 1)] = rt;
-        else a.worklist[a.worklist_cap - 1 - atomicAdd(&a.counters[3], 1)] = rt;
-      }
+    }
+  }
+  if (!deferred) return;
+  __syncthreads();
+  /* first touch of a (robot, tile) in this update appends it to the work list: 32 bitmap words per warp and step, one
+   * lane per tile of every non-empty word */
+  const int warp = threadIdx.x >> 5;
+  for (int base = 32 * warp; base < probe_words; base += (int)blockDim.x) {
+    const uint32_t mine = (base + lane < probe_words) ? s_probed[base + lane] : 0u;
+    for (unsigned nz = __ballot_sync(0xffffffffu, mine != 0u); nz; nz &= nz - 1u) {
+      const int src = __ffs(nz) - 1;
+      const uint32_t word = __shfl_sync(0xffffffffu, mine, src);
+      if ((word >> lane) & 1u)
+        himm_first_touch(a, rel * n_tiles + 32 * (base + src) + lane, ((s_heavy[base + src] >> lane) & 1u) != 0u);
     }
   }
 }
