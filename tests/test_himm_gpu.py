@@ -4,6 +4,8 @@ Reference behaviour under test: LaserMapUpdater::updateMap (move_control/src/las
 MapUpdater::lineOnMap/clearCell/markCell (move_control/include/move_control/map_updater.h:38-71),
 grid_map::LineIterator (grid_map_core/src/iterators/LineIterator.cpp).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -587,6 +589,7 @@ def test_free_block_summaries_never_claim_a_non_free_block(ctx):
             total += check("cycle %d" % c)
             for k in spots:
                 assert_layers_equal(dg.download("laser", robot=k), layers[k], "cycle %d robot %d" % (c, k))
-    if dg.layer_format("laser") == "coded":   # FLOAT layers only ever record whole tiles
+    # FLOAT layers only ever record whole tiles, and so does the multi-warp kernel when it is forced on a fleet
+    if dg.layer_format("laser") == "coded" and os.environ.get("B200NAV_MW_HEAVY") != "2":
         assert total > 100, "the summaries never recorded a free block"
     dg.close()
