@@ -654,6 +654,23 @@ def run_gpu_arm(args, rank, world, local_rank):
                                   "warp_instructions_per_visit": issue["warp_instructions_per_launch"] /
                                   max(float(np.mean([u[1] for u in used])), 1.0),
                                   "source": issue.get("source")}
+    # SURVEY 8d's second denominator: cell visits per second against the rate at which this GPU retires unordered
+    # 4-byte reductions at random addresses (measured in this run, outside the timed region) - the ceiling of a
+    # one-atomic-per-visit design.  The tile kernel uses no atomics per visit (every cell has one owner); the number
+    # says what that ordering-exact design costs or gains against the unordered one.
+    try:
+        red_l2 = arm.ctx.calibrate_red(32 << 20)
+        red_hbm = arm.ctx.calibrate_red(4 << 30)
+        visits_per_s = float(np.mean([u[1] for u in used])) / (tile_avg_ms / 1e3)
+        line["roofline_red"] = {"bound": "unordered L2 reductions (not used by this path)", "unit": "G/s",
+                                "visits_per_s": visits_per_s / 1e9,
+                                "red_peak_32MiB_buffer": red_l2 / 1e9, "red_peak_4GiB_buffer": red_hbm / 1e9,
+                                "visits_over_red_peak_32MiB": visits_per_s / red_l2,
+                                "visits_over_red_peak_4GiB": visits_per_s / red_hbm,
+                                "how": "b200nav_ctx_calibrate_red: RED.ADD.u32 at xorshift-random words, "
+                                       "148 x 8 CTAs x 256 threads x 256 reductions, CUDA events"}
+    except Exception as e:  # noqa: BLE001 - a measurement aid must not cost the bench line
+        line["roofline_red"] = {"error": str(e)[:200]}
     # the two smaller kernels against the same HBM peak (SURVEY section 8d accounting; both are latency bound)
     beams = float(np.mean([u[3] for u in used]))
     n_sub = int(math.ceil(arm.cfg["submap"] / arm.cfg["res"])) + 1

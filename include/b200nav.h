@@ -60,6 +60,10 @@ int b200nav_ctx_synchronize(b200nav_ctx* ctx);
 /* Measurement aid for bench.py: streams write_bytes (stores) and then read_bytes (loads) of scratch memory through
  * L2 on the context's stream so that a following step starts with a cold cache. */
 int b200nav_ctx_flush_l2(b200nav_ctx* ctx, size_t write_bytes, size_t read_bytes);
+/* Measurement aid for bench.py (SURVEY 8d's second roofline denominator): the rate at which the device retires
+ * unordered 4-byte reductions (RED.ADD) at uniformly random words of a scratch buffer of buffer_bytes (rounded down to a
+ * power of two; 32 MiB stays in L2, 4 GiB does not).  Synchronous; allocates and frees its scratch. */
+int b200nav_ctx_calibrate_red(b200nav_ctx* ctx, size_t buffer_bytes, double* reds_per_second);
 int b200nav_ctx_fence(b200nav_ctx* ctx, int* ticket);
 int b200nav_ctx_wait(b200nav_ctx* ctx, int ticket);
 void* b200nav_ctx_stream(b200nav_ctx* ctx);

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "b200nav_grid_layer_written": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "b200nav_grid_layer_devptr": (C.c_void_p, [C.c_void_p, C.c_char_p]),
     "b200nav_ctx_flush_l2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "b200nav_ctx_calibrate_red": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]),
     "b200nav_ctx_fence": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "b200nav_ctx_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_himm_update_cloud_batched_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -188,6 +189,12 @@ class Context:
 
     def flush_l2(self, write_bytes, read_bytes=0):
         check(lib().b200nav_ctx_flush_l2(self.h, int(write_bytes), int(read_bytes)), self.h)
+
+    def calibrate_red(self, buffer_bytes):
+        """Unordered 4-byte reductions per second at random words of a scratch buffer (measurement aid)."""
+        v = C.c_double()
+        check(lib().b200nav_ctx_calibrate_red(self.h, int(buffer_bytes), C.byref(v)), self.h)
+        return v.value
 
     def fence(self):
         """Mark the current end of the stream; returns a ticket for wait()."""

@@ -836,6 +836,42 @@ int b200nav_ctx_flush_l2(b200nav_ctx* ctx, size_t write_bytes, size_t read_bytes
   return B200NAV_OK; /* not counted in launch_count: a measurement aid, not part of the path */
 }
 
+int b200nav_ctx_calibrate_red(b200nav_ctx* ctx, size_t buffer_bytes, double* reds_per_second) {
+  if (!ctx || !reds_per_second || buffer_bytes < 4096) return B200NAV_EINVAL;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  size_t words = 1;
+  while (words * 2 * sizeof(unsigned) <= buffer_bytes) words *= 2; /* a power of two: the index is a mask */
+  if (words > (size_t)1 << 32) words = (size_t)1 << 32;
+  unsigned* buf = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&buf, words * sizeof(unsigned)));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = B200NAV_OK;
+  float ms = 0.0f;
+  const unsigned blocks = (unsigned)ctx->sm_count * 8;
+  const int iters = 256;
+  auto step = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == B200NAV_OK) rc = set_err(ctx, B200NAV_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  };
+  step(cudaMemsetAsync(buf, 0, words * sizeof(unsigned), ctx->stream), "cudaMemsetAsync");
+  step(cudaEventCreate(&e0), "cudaEventCreate");
+  step(cudaEventCreate(&e1), "cudaEventCreate");
+  if (rc == B200NAV_OK) {
+    red_calibration_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, (unsigned)(words - 1), iters, 1u); /* warm-up */
+    step(cudaEventRecord(e0, ctx->stream), "cudaEventRecord");
+    red_calibration_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, (unsigned)(words - 1), iters, 2u);
+    step(cudaEventRecord(e1, ctx->stream), "cudaEventRecord");
+    step(cudaGetLastError(), "red_calibration_kernel");
+    step(cudaEventSynchronize(e1), "cudaEventSynchronize");
+    step(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(buf);
+  if (rc != B200NAV_OK) return rc;
+  *reds_per_second = (double)blocks * 256.0 * (double)iters / ((double)ms * 1e-3);
+  return B200NAV_OK; /* not counted in launch_count: a measurement aid, not part of the path */
+}
+
 int b200nav_ctx_fence(b200nav_ctx* ctx, int* ticket) {
   if (!ctx || !ticket) return B200NAV_EINVAL;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));

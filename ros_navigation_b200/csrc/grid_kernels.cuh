@@ -133,5 +133,21 @@ __global__ void l2_flush_kernel(uint4* __restrict__ buf, size_t n16, int mode, u
   if (mode == 2 && acc == 0x9e3779b9u) *sink = acc; /* keeps the loads alive */
 }
 
+/* Measurement aid (bench.py): the rate at which this GPU retires UNORDERED 4-byte reductions (RED.ADD, no
+ * return value) at uniformly random words of a buffer - the ceiling of the obvious "one atomic per cell visit" design
+ * (which could not be exact anyway: clear and mark do not commute).  The tile kernel's visits per second are quoted
+ * against it. */
+__global__ void __launch_bounds__(256) red_calibration_kernel(unsigned* __restrict__ buf, unsigned word_mask, int iters,
+                                                              unsigned seed) {
+  unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + seed;
+#pragma unroll 8
+  for (int i = 0; i < iters; i++) {
+    x ^= x << 13; /* xorshift32 */
+    x ^= x >> 17;
+    x ^= x << 5;
+    atomicAdd(&buf[x & word_mask], 1u);
+  }
+}
+
 }  // namespace b200nav
 #endif

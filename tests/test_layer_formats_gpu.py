@@ -142,3 +142,15 @@ def test_both_tile_kernels_run_the_himm_suite(mode):
                           "or uneven or c2_sized",
                           "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_red_calibration_is_a_plain_measurement(ctx):
+    """b200nav_ctx_calibrate_red (bench.py's roofline_red): a positive, finite rate; rejects a useless buffer; a buffer
+    that fits L2 is not slower than one that does not."""
+    from ros_navigation_b200 import capi
+    small = ctx.calibrate_red(32 << 20)
+    big = ctx.calibrate_red(1 << 30)
+    assert np.isfinite(small) and np.isfinite(big) and small > 1e9 and big > 1e9
+    assert small > 0.8 * big
+    with pytest.raises(capi.B200NavError):
+        ctx.calibrate_red(16)
