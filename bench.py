@@ -695,8 +695,24 @@ def run_gpu_arm(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": cpu.n * n_cyc / secs, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
                                     "sample": ("%d robots x %d cycles of workload %s (%.1f s); " + cpu.parts) % (
                                         cpu.n, n_cyc, args.workload, secs)}
+            if cpu.kind == "reference":
+                # beside the reference as written (per-cell string-keyed layer lookup, master copy, submap
+                # copy of all layers) also the restatement with those hoisted: oracle HIMM + pseudo-scan + reference
+                # vfh.cpp, one Python thread per core around native calls (a shorter sample: ~4 s)
+                del cpu
+                os.environ["B200NAV_CPU_PORT"] = "1"
+                try:
+                    port = CpuArm(args.workload, cpu_sample_size(args.workload))
+                    t_cal = port.run_cycle(0)
+                    n_cyc = int(max(2, min(500, 4.0 / max(t_cal, 1e-3))))
+                    secs = sum(port.run_cycle(1 + k) for k in range(n_cyc))
+                    line["cpu_baseline"]["hoisted_port"] = {
+                        "value": port.n * n_cyc / secs, "cores": port.cores,
+                        "sample": ("%d robots x %d cycles (%.1f s); " + port.parts) % (port.n, n_cyc, secs)}
+                finally:
+                    del os.environ["B200NAV_CPU_PORT"]
         except Exception as e:  # the baseline must never take the GPU number down
-            line["cpu_baseline"] = {"error": repr(e)}
+            line.setdefault("cpu_baseline", {})["error"] = repr(e)
     if cold is not None:
         line["cold_grid"] = cold
     if sharded is not None:
