@@ -690,7 +690,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         try:
             cpu = CpuArm(args.workload, cpu_sample_size(args.workload))
             t_cal = cpu.run_cycle(0)
-            n_cyc = int(max(2, min(2000, 12.0 / max(t_cal, 1e-3))))
+            n_cyc = int(max(2, min(4000, 20.0 / max(t_cal, 1e-3))))   # the first (cold) cycle overestimates: lands at 10-15 s
             secs = sum(cpu.run_cycle(1 + k) for k in range(n_cyc))
             line["cpu_baseline"] = {"value": cpu.n * n_cyc / secs, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
                                     "sample": ("%d robots x %d cycles of workload %s (%.1f s); " + cpu.parts) % (
