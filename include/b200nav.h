@@ -77,6 +77,11 @@ int64_t b200nav_ctx_launch_count(b200nav_ctx* ctx);
  * "himm_tile_mw", "vfh_update"), the summed device time in milliseconds and the number of timed launches. */
 int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable);
 int b200nav_ctx_profile_read(b200nav_ctx* ctx, const char* name, double* total_ms, int64_t* launches);
+/* Restricts the timing to the kernels named in the comma-separated list (NULL or "": all, the default).  Every timed
+ * launch costs two event records on the stream, which keep the next kernel's launch from overlapping the previous
+ * kernel's tail (measured: 0.016 ms per three-kernel cycle): bench.py times only the dominant kernel inside its timed
+ * steps and all of them in a separate pass. */
+int b200nav_ctx_profile_select(b200nav_ctx* ctx, const char* names);
 
 /* ------------------------------------------------------------------------------------------------------
  * Grid: device-resident grid_map::GridMap layers for n_robots independent maps of identical size.

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "b200nav_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "b200nav_ctx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "b200nav_ctx_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "b200nav_ctx_profile_select": (C.c_int, [C.c_void_p, C.c_char_p]),
     "b200nav_himm_last_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200nav_himm_update_cloud_batched": (C.c_int, [C.c_void_p, C.c_char_p] + [C.c_void_p] * 5),
     "b200nav_himm_update_cloud_batched_dev": (C.c_int, [C.c_void_p, C.c_char_p] + [C.c_void_p] * 4 + [C.c_int, C.c_int]),
@@ -216,6 +217,11 @@ class Context:
 
     def profile_enable(self, on=True):
         check(lib().b200nav_ctx_profile_enable(self.h, int(on)), self.h)
+
+    def profile_select(self, names=None):
+        """Time only the named kernels (iterable of names; None: all) while profiling is enabled."""
+        arg = ",".join(names).encode() if names else None
+        check(lib().b200nav_ctx_profile_select(self.h, arg), self.h)
 
     def profile_read(self, name):
         """(total device ms, timed launches) of kernel `name` since profile_enable(True)."""

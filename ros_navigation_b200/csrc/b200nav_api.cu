@@ -49,6 +49,7 @@ struct b200nav_ctx {
   int64_t launches = 0;
   int sm_count = 0;
   bool profiling = false;
+  unsigned prof_mask = ~0u;                /* kernel kinds that are timed while profiling (b200nav_ctx_profile_select) */
   cudaStream_t copy_stream = nullptr;      /* host->device copies pipelined with the prep kernel */
   std::vector<cudaEvent_t> copy_events;
   bool prep_done_valid = false;            /* copy_events[6] = "the last binning kernel has consumed the staged cloud" */
@@ -272,7 +273,7 @@ struct ProfScope {
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
   cudaStream_t st;
   ProfScope(b200nav_ctx* c, int k, cudaStream_t stream = nullptr) : ctx(c), kind(k), st(stream ? stream : c->stream) {
-    if (!ctx->profiling) return;
+    if (!ctx->profiling || !((ctx->prof_mask >> kind) & 1u)) return;
     ProfSlot& s = ctx->prof[kind];
     if (!s.free_pairs.empty()) {
       ev = s.free_pairs.back();
@@ -922,6 +923,30 @@ int b200nav_ctx_profile_enable(b200nav_ctx* ctx, int enable) {
       ctx->prof[k].total_ms = 0;
       ctx->prof[k].count = 0;
     }
+  return B200NAV_OK;
+}
+
+int b200nav_ctx_profile_select(b200nav_ctx* ctx, const char* names) {
+  if (!ctx) return B200NAV_EINVAL;
+  if (!names || !*names) {
+    ctx->prof_mask = ~0u;
+    return B200NAV_OK;
+  }
+  unsigned mask = 0u;
+  const char* p = names;
+  while (*p) {
+    const char* e = strchr(p, ',');
+    const size_t len = e ? (size_t)(e - p) : strlen(p);
+    bool found = false;
+    for (int k = 0; k < PROF_KINDS; k++)
+      if (strlen(kProfNames[k]) == len && strncmp(p, kProfNames[k], len) == 0) {
+        mask |= 1u << k;
+        found = true;
+      }
+    if (!found) return set_err(ctx, B200NAV_EINVAL, "profile_select: unknown kernel name in '%s'", names);
+    p += len + (e ? 1 : 0);
+  }
+  ctx->prof_mask = mask;
   return B200NAV_OK;
 }
 
