@@ -706,6 +706,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     # ---- CPU baseline on a bounded sample (rank 0, N == 1 only) ----
     if world == 1 and not args.no_cpu:
         try:
+            os.sched_setaffinity(0, args.full_affinity)   # the CPU arm uses all host cores
             cpu = CpuArm(args.workload, cpu_sample_size(args.workload))
             t_cal = cpu.run_cycle(0)
             n_cyc = int(max(2, min(4000, 20.0 / max(t_cal, 1e-3))))   # the first (cold) cycle overestimates: lands at 10-15 s
@@ -731,6 +732,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                     del os.environ["B200NAV_CPU_PORT"]
         except Exception as e:  # the baseline must never take the GPU number down
             line.setdefault("cpu_baseline", {})["error"] = repr(e)
+        pin_to_gpu_numa_node(local_rank)   # back next to the GPU for the remaining GPU legs
     if cold is not None:
         line["cold_grid"] = cold
     if sharded is not None:
@@ -959,7 +961,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
-    args.cpu_affinity = pin_to_gpu_numa_node(local_rank) if world > 1 else "unchanged (single rank)"
+    # the GPU legs run on the CPUs next to the GPU (pinned buffers, enqueue thread); the CPU baseline leg gets every
+    # host core back (run_gpu_arm restores args.full_affinity before it starts its threads)
+    args.full_affinity = os.sched_getaffinity(0)
+    args.cpu_affinity = pin_to_gpu_numa_node(local_rank)
 
     import torch
     if not torch.cuda.is_available():
