@@ -586,7 +586,13 @@ def run_gpu_arm(args, rank, world, local_rank):
                 sharded[name] = {"error": repr(e)}
     total_ms = float(sum(ms))
     t = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=device)
+    by_rank = None
     if world > 1:
+        mine = torch.tensor([total_ms / args.steps, tile_ms / max(tile_n, 1)], dtype=torch.float64, device=device)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        by_rank = {"ms_per_step": [round(float(e[0]), 4) for e in every],
+                   "tile_kernel_ms": [round(float(e[1]), 4) for e in every]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
     value = robots_total * args.steps / (total_ms / 1000.0)
@@ -644,7 +650,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                                       "launch overlap)",
                                "all_kernels_timed_pass": {"ms_per_step": sum(ms_all_timed) / max(len(ms_all_timed), 1),
                                                           "himm_tile": tile2_ms / max(tile2_n, 1)}},
-        "wall_s_timed_region": wall,
+        "wall_s_timed_region": wall, "by_rank": by_rank,
         "host_enqueue_ms_per_step": getattr(arm, "host_enqueue_ms_per_step", None),
         "e2e_host_enqueue_ms_per_step": e2e_enqueue_ms, "cpu_affinity": args.cpu_affinity,
         "exchange_verified": (None if exchange_bad is None else
