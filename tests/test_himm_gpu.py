@@ -486,6 +486,21 @@ def test_c3_sized_grid_few_scans(ctx):
     dg.close()
 
 
+def test_grid_with_more_tiles_than_the_binning_bitmap(ctx):
+    """9024 x 8320 cells = 141 x 130 = 18 330 tiles per robot: more than the binning kernel's per-CTA tile bitmap
+    (16 384), so every first-touch probe goes straight to global memory; also not a whole number of tiles in x."""
+    rng = np.random.default_rng(77)
+    g, dg = make_pair(ctx, 180.48, 166.4, 0.02)
+    layer = O.new_layer(g)
+    for step, origin in enumerate([(10.0, -20.0), (-60.0, 55.0), (85.0, 80.0)]):
+        s = lidar_samples(rng, g, origin, 2000, 0.5, 70.0, clear_frac=0.1)
+        O.himm_update(g, layer, s)
+        dg.himm_update("laser", s)
+    assert_layers_equal(dg.download("laser"), layer, "large-grid sequence")
+    assert np.nansum(layer) > 0
+    dg.close()
+
+
 def test_c4_full_size_properties(ctx):
     """BASELINE config 4 at full size (1024 robots x 512 x 512, device-resident samples): spot robots are compared
     with the oracle bit-for-bit; all robots satisfy the size-independent HIMM invariants (value set {NaN,0..180}
