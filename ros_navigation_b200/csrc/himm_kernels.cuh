@@ -549,13 +549,15 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
       constexpr int RINGS = 4;
       auto ring_block = [&](const int k, int& off, unsigned& frac) {
         int offs[RINGS];
-        int val[RINGS]; /* my cell of ring r as read (a value >= 2 counts visits); 0 when I am not on the ring */
+        /* my cell of ring r as read: a value >= 2 counts visits, 0 (NaN) becomes free on any visit, 1 is free already
+         * and needs no store; -1 when I am not on the ring */
+        int val[RINGS];
         bool sens = mark_k >= 0 && (unsigned)(mark_k - k) < (unsigned)RINGS; /* I mark inside this block */
 #pragma unroll
         for (int r = 0; r < RINGS; r++) {
           offs[r] = off;
           const bool on = (unsigned)(k + r) <= span;
-          val[r] = on ? view.peek(off) : 0;
+          val[r] = on ? view.peek(off) : -1;
           sens = sens || val[r] >= 2;
           const unsigned nf = frac + my_S;
           off += (nf < frac) ? step_carry : step_plain;
@@ -565,13 +567,13 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
         if (!__any_sync(0xffffffffu, sens)) {
 #pragma unroll
           for (int r = 0; r < RINGS; r++)
-            if ((unsigned)(k + r) <= span) view.set_free(offs[r]);
+            if (val[r] == 0) view.set_free(offs[r]);
         } else {
           /* match.any costs issue time in proportion to the number of DISTINCT keys in the warp (measured on B200:
            * ~4 cycles for one key, 31-83 for 32): lanes that are not on the ring share one key. */
 #pragma unroll
           for (int r = 0; r < RINGS; r++) {
-            const bool on = (unsigned)(k + r) <= span, marking = k + r == mark_k;
+            const bool on = val[r] >= 0, marking = k + r == mark_k;
             if (__any_sync(0xffffffffu, val[r] >= 2 || (on && marking))) {
               const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1);
               const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
@@ -579,7 +581,7 @@ __device__ __forceinline__ void himm_apply_list(const View view, const int pitch
                 if (marks == 0u) view.clear_n_known(offs[r], val[r], __popc(group));
                 else view.clear_seq_known(offs[r], val[r], group, marks);
               }
-            } else if (on) {
+            } else if (val[r] == 0) {
               view.set_free(offs[r]);
             }
           }
@@ -1305,7 +1307,7 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
         for (int r = 0; r < RINGS; r++) {
           offs[r] = off;
           const bool on = (unsigned)(k + r) <= span;
-          val[r] = on ? view.peek(off) : 0;
+          val[r] = on ? view.peek(off) : -1;
           sens = sens || val[r] >= 2;
           const unsigned nf = frac + my_S;
           off += (nf < frac) ? step_carry : step_plain;
@@ -1315,11 +1317,11 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
         if (!__any_sync(0xffffffffu, sens)) {
 #pragma unroll
           for (int r = 0; r < RINGS; r++)
-            if ((unsigned)(k + r) <= span) view.set_free(offs[r]);
+            if (val[r] == 0) view.set_free(offs[r]);
         } else {
 #pragma unroll
           for (int r = 0; r < RINGS; r++) {
-            const bool on = (unsigned)(k + r) <= span, marking = k + r == mark_k;
+            const bool on = val[r] >= 0, marking = k + r == mark_k;
             if (__any_sync(0xffffffffu, val[r] >= 2 || (on && marking))) {
               const unsigned group = __match_any_sync(0xffffffffu, on ? offs[r] : -1);
               const unsigned marks = __ballot_sync(0xffffffffu, on && marking) & group;
@@ -1327,7 +1329,7 @@ __device__ __forceinline__ void himm_apply_list_pipe(const CodeView view, const 
                 if (marks == 0u) view.clear_n_known(offs[r], val[r], __popc(group));
                 else view.clear_seq_known(offs[r], val[r], group, marks);
               }
-            } else if (on) {
+            } else if (val[r] == 0) {
               view.set_free(offs[r]);
             }
           }
