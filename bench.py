@@ -386,8 +386,10 @@ class GpuArm:
                 # N > 1 without torch in the loop: inputs up, VFH+ kernel, NCCL all-gather and the copy of the whole
                 # fleet's table to pinned host memory are ONE enqueue-only library call on side streams
                 from ros_navigation_b200.capi import check, lib
-                if k >= 2:
+                if k >= 2:   # blocks until the slot's previous cycle is on the host: a wait, not enqueue work
+                    t_w = time.perf_counter()
                     check(lib().b200nav_fleet_cycle_wait(self.exchange.fleet, slot), self.ctx.h)
+                    busy -= time.perf_counter() - t_w
                 check(lib().b200nav_fleet_cycle_async(self.exchange.fleet, self.vfh.h, self.grid.h, b"master",
                                                       self.h_inputs[c].data_ptr(), slot, self.h_cmds[slot].data_ptr()),
                       self.ctx.h)
@@ -588,11 +590,16 @@ def run_gpu_arm(args, rank, world, local_rank):
     t = torch.tensor([total_ms, e2e_s * 1000.0], dtype=torch.float64, device=device)
     by_rank = None
     if world > 1:
-        mine = torch.tensor([total_ms / args.steps, tile_ms / max(tile_n, 1)], dtype=torch.float64, device=device)
+        mine = torch.tensor([total_ms / args.steps, tile_ms / max(tile_n, 1),
+                             getattr(arm, "host_enqueue_ms_per_step", 0.0) or 0.0, e2e_enqueue_ms,
+                             e2e_s * 1000.0 / args.steps], dtype=torch.float64, device=device)
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
         by_rank = {"ms_per_step": [round(float(e[0]), 4) for e in every],
-                   "tile_kernel_ms": [round(float(e[1]), 4) for e in every]}
+                   "tile_kernel_ms": [round(float(e[1]), 4) for e in every],
+                   "host_enqueue_ms_per_step": [round(float(e[2]), 4) for e in every],
+                   "e2e_host_enqueue_ms_per_step": [round(float(e[3]), 4) for e in every],
+                   "e2e_ms_per_step": [round(float(e[4]), 4) for e in every]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
     value = robots_total * args.steps / (total_ms / 1000.0)
