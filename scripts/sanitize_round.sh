@@ -20,3 +20,11 @@ run synccheck synccheck B200NAV_MW_HEAVY=1
 run racecheck racecheck B200NAV_MW_HEAVY=0
 run racecheck_mw racecheck B200NAV_MW_HEAVY=1
 tail -n 8 gpurun_out/sanitizer_*_${TAG}.log
+# the GPU test suite itself under memcheck (everything but the subprocess-spawning tests) and the HIMM + VFH+ tests
+# under racecheck with one warp per tile
+timeout 1200 compute-sanitizer --tool memcheck --print-limit 10 python -m pytest tests -m gpu -q -k "not bench_contract and not fleet" > gpurun_out/sanitizer_memcheck_suite_${TAG}.full 2>&1
+B200NAV_MW_HEAVY=0 timeout 1200 compute-sanitizer --tool racecheck --print-limit 10 python -m pytest tests/test_himm_gpu.py tests/test_vfh_gpu.py -m gpu -q -k "not c2_sized and not c3_sized and not c4_full and not more_tiles" > gpurun_out/sanitizer_racecheck_suite_${TAG}.full 2>&1
+for n in memcheck_suite racecheck_suite; do
+  grep -E "passed|failed|ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/sanitizer_${n}_${TAG}.full > gpurun_out/sanitizer_${n}_${TAG}.log
+  cat gpurun_out/sanitizer_${n}_${TAG}.log
+done
