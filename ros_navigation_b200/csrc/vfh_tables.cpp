@@ -1,6 +1,13 @@
 /*
  * vfh_tables.cpp -- see vfh_tables.h.  Pure host C++ (compiled by g++, not nvcc, so that <math.h> overloads
  * resolve exactly as in the reference build).
+ *
+ * Provenance: the tables must be bit-identical to the ones the reference's VFH::Init builds, so the arithmetic
+ * expressions below (the quadrant ladder of cell directions, `atanf(..) * (360.0 / 6.28)`, the magnitude polynomial,
+ * the sector-overlap test) follow move_control/src/vfh.cpp:237-416 expression by expression; the layout, the bitmask
+ * form of the sector lists and everything else are this project's.  The reference file derives from the Player / Orca
+ * VFH+ driver (Orca-Components, copyright 2004) and is distributed under the GNU General Public License, version 2
+ * or later; whoever ships this file with a product inherits that obligation for it.
  */
 #include "vfh_tables.h"
 
