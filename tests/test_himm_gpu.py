@@ -608,3 +608,32 @@ def test_free_block_summaries_never_claim_a_non_free_block(ctx):
     if dg.layer_format("laser") == "coded" and os.environ.get("B200NAV_MW_HEAVY") != "2":
         assert total > 100, "the summaries never recorded a free block"
     dg.close()
+
+
+def test_random_geometries_and_boundary_endpoints(ctx):
+    """The GPU side of tests/test_reference_pin.py::test_himm_core_random_geometries_and_boundary_endpoints:
+    resolutions that do not divide the lengths, far-away map centres, end points exactly on cell borders."""
+    rng = np.random.default_rng(20261017)
+    for case in range(16):
+        lx, ly = rng.uniform(0.6, 9.0, 2)
+        res = float(rng.choice([0.05, 0.03, 0.07, 0.1, 0.125, 0.02]))
+        px, py = rng.uniform(-2000.0, 2000.0, 2)
+        g, dg = make_pair(ctx, float(lx), float(ly), res, (float(px), float(py)))
+        layer = O.new_layer(g)
+        Lx, Ly = g.rows * res, g.cols * res
+        for it in range(4):
+            n = 160
+            s = random_samples(rng, g, n, spread=0.97, clear_frac=0.25)
+            kx, ky = rng.integers(0, g.rows + 1, n), rng.integers(0, g.cols + 1, n)
+            on_border = rng.random(n) < 0.34
+            s["ex"] = np.where(on_border, (px + Lx / 2) - kx * res, s["ex"])
+            s["ey"] = np.where(on_border, (py + Ly / 2) - ky * res, s["ey"])
+            outside = rng.random(n) < 0.3
+            s["ex"] = np.where(outside & ~on_border, px + (rng.random(n) - 0.5) * Lx * 2.2, s["ex"])
+            s["ey"] = np.where(outside & ~on_border, py + (rng.random(n) - 0.5) * Ly * 2.2, s["ey"])
+            b1, b2 = np.zeros(4), np.zeros(4)
+            O.himm_update(g, layer, s, b1)
+            dg.himm_update("laser", s, bbox=b2)
+            assert np.array_equal(b1, b2), "bbox, case %d" % case
+        assert_layers_equal(dg.download("laser"), layer, "case %d: %r x %r @ %r at (%r, %r)" % (case, lx, ly, res, px, py))
+        dg.close()

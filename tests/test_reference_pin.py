@@ -247,3 +247,42 @@ def test_steer_goal_glue_matches_reference_steerer():
         compared += 1
     assert done[0] == 1 and compared > 100 and idx[0] == len(plan)
     node.close()
+
+
+def test_himm_core_random_geometries_and_boundary_endpoints():
+    """Property test of the same pin: geometries the fixed cases do not reach (resolutions that do not divide the
+    lengths, far-away map centres, thin maps) and end points placed EXACTLY on cell borders (multiples of the
+    resolution from the map corner), where the two association orders of the index arithmetic and the truncation
+    toward zero decide the cell."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(st.floats(0.6, 9.0), st.floats(0.6, 9.0), st.sampled_from([0.05, 0.03, 0.07, 0.1, 0.125, 0.02]),
+           st.floats(-2000.0, 2000.0), st.floats(-2000.0, 2000.0), st.integers(0, 2 ** 31 - 1))
+    def check(lx, ly, res, px, py, seed):
+        rng = np.random.default_rng(seed)
+        g = O.make_geom(lx, ly, res, px, py)
+        core = N.Core(lx, ly, res, (px, py))
+        assert (core.rows, core.cols) == (g.rows, g.cols)
+        layer = O.new_layer(g)
+        Lx, Ly = g.rows * res, g.cols * res
+        for it in range(4):
+            n = 120
+            s = random_samples(rng, g, n, spread=0.97, clear_frac=0.25)     # starts inside the map
+            # a third of the end points exactly on cell borders (also on the map's outer border), a third outside
+            kx, ky = rng.integers(0, g.rows + 1, n), rng.integers(0, g.cols + 1, n)
+            on_border = rng.random(n) < 0.34
+            s["ex"] = np.where(on_border, (px + Lx / 2) - kx * res, s["ex"])
+            s["ey"] = np.where(on_border, (py + Ly / 2) - ky * res, s["ey"])
+            outside = rng.random(n) < 0.3
+            s["ex"] = np.where(outside & ~on_border, px + (rng.random(n) - 0.5) * Lx * 2.2, s["ex"])
+            s["ey"] = np.where(outside & ~on_border, py + (rng.random(n) - 0.5) * Ly * 2.2, s["ey"])
+            b1, b2 = np.zeros(4), np.zeros(4)
+            O.himm_update(g, layer, s, b1)
+            core.update(s, b2)
+            assert np.array_equal(b1, b2)
+        assert_layers_equal(core.layer(), layer, "lx=%r ly=%r res=%r pos=(%r, %r) seed=%d" % (lx, ly, res, px, py, seed))
+        core.close()
+
+    check()
